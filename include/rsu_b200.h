@@ -1,0 +1,182 @@
+/*
+ * rsu_b200.h -- C ABI of the B200-native U-Net hot path (librsu_b200.so).
+ *
+ * The reference (aschneuw/road-segmentation-unet) has no FFI: its boundary is TensorFlow's
+ * Session.run() into stock op kernels (src/tf_aerial_images.py:241-244, :312) plus NumPy/SciPy
+ * helpers (src/images.py).  Every entry point below replaces one such op (or one NumPy helper)
+ * and cites the reference call site it stands in for.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says "host"; the caller owns every buffer;
+ *   - activations are NHWC bf16, described by rsu_view (element strides, so channel slices and
+ *     crops of a larger tensor are expressed without copies);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, otherwise an RSU_E* code; rsu_last_error() gives the message.
+ *   - there is no CPU fallback: unsupported shapes are errors.
+ */
+#ifndef RSU_B200_H
+#define RSU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSU_OK 0
+#define RSU_EINVAL 1  /* bad shape / unsupported configuration            */
+#define RSU_EALIGN 2  /* pointer or stride violates an alignment rule      */
+#define RSU_ECUDA 3   /* CUDA runtime / driver error                       */
+#define RSU_ENODEV 4  /* no sm_100 device                                  */
+
+#define RSU_MAX_SRC 4
+#define RSU_MAX_TAPS 9
+
+const char* rsu_last_error(void);
+int rsu_version(void);
+/* Number of kernels launched by this library since load / since the last reset. */
+long long rsu_launch_count(void);
+void rsu_reset_launch_count(void);
+
+/* NHWC bf16 activation view: element (n, y, x, c) lives at ptr + n*sn + y*sy + x*sx + c. */
+typedef struct {
+  const void* ptr;
+  int C, H, W, N;       /* extents of this view (C % 64 == 0 for GEMM operands) */
+  long long sn, sy, sx; /* strides in ELEMENTS (sx % 8 == 0)                    */
+  int off_y, off_x;     /* offset added to the output pixel coordinate (crop)   */
+} rsu_view;
+
+/* ---------------------------------------------------------------- tcgen05 implicit GEMM ---- */
+
+/* Generic implicit-GEMM convolution on the 5th-gen tensor cores:
+ *   out[n, y, x, co] = epilogue( sum_{tap, src, c} src[n, y+dy[tap]+off_y, x+dx[tap]+off_x, c]
+ *                                                  * weights[co][(tap, src, c)] )
+ * Replaces tf.layers.conv2d / Conv2DBackpropInput (unet.py:34-45, 88-91) including the crop +
+ * concat of unet.py:70-85 (several sources walked by the K loop) and, with shuffle_cout > 0,
+ * tf.layers.conv2d_transpose k=2 s=2 (unet.py:67): GEMM column (a, b, co) is stored at output
+ * pixel (2y+a, 2x+b).  Out-of-range source pixels read as zero (used by the data gradients). */
+typedef struct {
+  int n_src;
+  rsu_view src[RSU_MAX_SRC];
+  int n_taps;
+  int tap_dy[RSU_MAX_TAPS], tap_dx[RSU_MAX_TAPS];
+  const void* weights; /* bf16 [Ntot][Ktot], Ktot = n_taps * sum(src.C), K contiguous */
+  int Ntot;
+  int H_out, W_out, N_img; /* GEMM pixel grid */
+  void* out;               /* bf16 */
+  long long out_sn, out_sy, out_sx;
+  int shuffle_cout;  /* 0, or Cout of a 2x2/s2 transpose conv (Ntot == 4*shuffle_cout) */
+  const float* bias; /* fp32 [Ntot] ([shuffle_cout] when shuffling) or NULL */
+  int relu;
+  const void* mask; /* bf16, same indexing as out with its own strides: keep where mask > 0 */
+  long long mask_sn, mask_sy, mask_sx;
+  int accumulate; /* out += result */
+} rsu_conv_gemm_desc;
+int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream);
+
+/* Weight gradient on the tensor cores (Conv2DBackpropFilter, unet.py:34-45,67,88-91):
+ *   out[(tap, src, c), co] += sum_{n,y,x} src[n, y+dy+off_y, x+dx+off_x, c] * grad[n, y+goff, x+goff, co]
+ * out is fp32 [n_taps*sum(src.C), Cout] -- i.e. TensorFlow's HWIO kernel layout -- and must be
+ * zero-initialised by the caller (partial sums over pixel splits are combined with atomics). */
+typedef struct {
+  int n_src;
+  rsu_view src[RSU_MAX_SRC];
+  int n_taps;
+  int tap_dy[RSU_MAX_TAPS], tap_dx[RSU_MAX_TAPS];
+  rsu_view grad;  /* C = Cout; off_y/off_x offset the grad pixel coordinate */
+  int H, W, N_img; /* pixel grid that is summed over */
+  float* out;
+  int ldo; /* row stride of out (>= grad.C) */
+} rsu_wgrad_desc;
+int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream);
+
+/* ---------------------------------------------------------------- weight packing ---------- */
+/* fp32 in[T][R][C] -> bf16 out[C][ld] with out[c][t*R + r] (transpose of every [R][C] slab; conv
+ * forward weights: HWIO [taps][Cin][Cout] -> [Cout][taps][Cin]).  ld = 0 means T*R; a larger ld
+ * leaves the tail of every output row untouched (zero padding of the Cin = 3 layers). */
+int rsu_pack_transpose(const float* in, void* out, int T, int R, int C, int ld, void* stream);
+/* fp32 in[T][R][C] -> bf16 out[R][T'][C] with T' = perm[T] (conv data-gradient weights:
+ * HWIO -> [Cin][tap'][Cout]; perm NULL = identity). */
+int rsu_pack_permute(const float* in, void* out, int T, int R, int C, const int* perm_host,
+                     void* stream);
+/* fp32 -> bf16 cast (transpose-conv forward weights keep TensorFlow's [kh][kw][Cout][Cin]). */
+int rsu_cast_bf16(const float* in, void* out, long long n, void* stream);
+
+/* ---------------------------------------------------------------- fused elementwise ------- */
+/* color_space_adjust (unet.py:22-23) + optional dropout (unet.py:29-30) + im2col of the 3x3
+ * (dilation d) neighbourhood into 64 bf16 channels (27 used, k = tap*3 + c):
+ *   net0 = (img - 0.5) @ W1 + b1 ; out[n, y, x, tap*3+c] = net0[n, y+oy+dy*d, x+ox+dx*d, c] */
+int rsu_color_im2col(const float* img, int N, int S, const float* w1 /* device [3][3] */,
+                     const float* b1 /* device [3] */, int dilation, int oy, int ox, int Ho, int Wo,
+                     void* out /* bf16 [N,Ho,Wo,64] */, float keep, unsigned long long seed,
+                     void* stream);
+/* Gradient of the block above w.r.t. W1/b1 given d(im2col) (bf16 [N,Ho,Wo,64]):
+ * accumulates dW1 [3][3], db1 [3] (fp32, atomics). */
+int rsu_color_im2col_bwd(const float* img, int N, int S, const void* dcol, int dilation, int oy,
+                         int ox, int Ho, int Wo, float* dw1, float* db1, float keep,
+                         unsigned long long seed, void* stream);
+
+/* 2x2/2 max-pool, NHWC bf16 (tf.layers.max_pooling2d, unet.py:52). */
+int rsu_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, void* stream);
+
+/* Gradient into a skip tensor Y [N,H,W,C] (ReLU output that feeds both the pool and the decoder
+ * crop, unet.py:47-52,70-85):  dZ = [Y>0] * ( maxpool_bwd(dP)  +  pad(dCrop) ).
+ * dP [N,H/2,W/2,C] may be NULL; dCrop is a view of the concat gradient (may be NULL) placed at
+ * (crop_y, crop_x).  Gradient goes to the first maximum of each window (ties are zeros). */
+int rsu_skip_grad(const void* Y, int N, int H, int W, int C, const void* dP, const rsu_view* dCrop,
+                  int crop_y, int crop_x, void* dZ, void* stream);
+
+/* dZ = [Y>0] * dY for strided views (ReluGrad). */
+int rsu_relu_mask(const rsu_view* Y, const rsu_view* dY, void* dZ, void* stream);
+
+/* Column sums of a bf16 view: out[c] += sum_{n,y,x} v[n,y,x,c]  (BiasAddGrad). */
+int rsu_bias_grad(const rsu_view* v, float* out, void* stream);
+
+/* Head (unet.py:95 + tf_aerial_images.py:103-110,147-148): 1x1 conv C->2, softmax, P(road),
+ * mean cross-entropy and -- when labels != NULL -- the gradients: dZ (bf16, ReLU-masked grad of
+ * the activation), dW [C][2], db [2], loss_sum (fp32 scalar, sum over pixels / (N*H*W)). */
+int rsu_head(const void* act, int N, int H, int W, int C, const float* w /*[C][2]*/,
+             const float* b /*[2]*/, const unsigned char* labels /* [N,H,W] or NULL */,
+             float* probs /* [N,H,W] or NULL */, float* logits /* [N,H,W,2] or NULL */,
+             float* loss /* scalar accumulate */, void* dZ, float* dW, float* db, void* stream);
+
+/* Inverted dropout on a bf16 tensor with a counter-based RNG (tf.nn.dropout, unet.py:30,65):
+ * y = x / keep * floor(keep + U);  the same (seed, site) regenerates the mask for backward. */
+int rsu_dropout(const void* x, void* y, long long n, float keep, unsigned long long seed,
+                void* stream);
+
+/* The scale factors (0 or 1/keep) rsu_dropout applies, as fp32 -- lets a test feed the identical
+ * mask to the CPU oracle (TensorFlow's own random stream is not reproducible). */
+int rsu_dropout_mask(float* m, long long n, float keep, unsigned long long seed, void* stream);
+
+/* Momentum SGD (tf.train.MomentumOptimizer, tf_aerial_images.py:116-121), fp32 master weights:
+ *   acc = momentum*acc + g*gscale ; w -= lr*acc */
+int rsu_momentum_sgd(float* w, float* acc, const float* g, long long n, float lr, float momentum,
+                     float gscale, void* stream);
+
+/* ---------------------------------------------------------------- geometry (images.py) ---- */
+/* images.mirror_border (images.py:269-281): np.pad(..., "symmetric") on H and W; fp32. */
+int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* out, void* stream);
+/* One element of the dihedral group per image: op = flip_ud (bit 2) then rot90^k (bits 0-1),
+ * counter-clockwise like np.rot90 / tf.image.rot90 (images.py:376-417,
+ * tf_aerial_images.py:173-210).  esize = bytes per pixel element group (C*sizeof). */
+int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
+                     const unsigned char* ops /* device [N] */, void* stream);
+/* images.extract_patches (images.py:35-85): x-outer / y-inner patch order; fp32. */
+int rsu_extract_patches(const float* in, int N, int H, int W, int C, int patch, int stride,
+                        float* out, void* stream);
+/* images.images_from_patches (images.py:131-164): overlap average in gather form. */
+int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int stride,
+                        float* out, void* stream);
+/* crop_imgs(rotate_imgs(x, angle), crop) (images.py:313-373): nearest-neighbour rotation with
+ * scipy.ndimage.rotate(order=0, reshape=True, cval=0) semantics followed by the centre crop.
+ * cos_a / sin_a are the host-computed cosine / sine of the angle (scipy uses cosdg / sindg). */
+int rsu_rotate_nn_crop(const float* in, int N, int H, int C, double cos_a, double sin_a, int crop,
+                       float* out, void* stream);
+/* invert_image_augmentation_ensemble (images.py:399-417): average of the 6 un-transformed masks. */
+int rsu_ensemble_invert(const float* masks /* [6N,S,S] */, int N, int S, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSU_B200_H */

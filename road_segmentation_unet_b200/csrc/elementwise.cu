@@ -1,0 +1,693 @@
+// HBM-bound fused elementwise / reduction kernels of the U-Net hot path (sm_100a).
+// All activations are NHWC bf16; every thread moves 16-byte vectors (8 bf16) so that a warp
+// covers 512 contiguous bytes.  Reference ops are cited per kernel.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace rsu {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = bf16_lo(w[e]);
+    f[2 * e + 1] = bf16_hi(w[e]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+// Counter-based uniform in [0,1): splitmix64 of (seed, index); 24 random bits.
+__host__ __device__ __forceinline__ float uniform01(unsigned long long seed,
+                                                    unsigned long long idx) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+}
+// tf.nn.dropout keeps an element iff floor(keep + U) == 1
+__host__ __device__ __forceinline__ float keep_scale(unsigned long long seed,
+                                                     unsigned long long idx, float keep) {
+  return (keep + uniform01(seed, idx) >= 1.0f) ? 1.0f / keep : 0.0f;
+}
+
+// ------------------------------------------------------------------ weight packing
+__global__ void pack_transpose_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                      int T, int R, int C, int ld) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[i][threadIdx.x] = in[(static_cast<long long>(t) * R + r) * C + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C)
+      out[static_cast<long long>(c) * ld + t * R + r] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+struct Perm {
+  int v[16];
+};
+__global__ void pack_permute_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                    int T, int R, int C, Perm perm) {
+  const long long total = 1LL * T * R * C;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long tr = i / C;
+    const int r = static_cast<int>(tr % R);
+    const int t = static_cast<int>(tr / R);
+    out[(static_cast<long long>(r) * T + perm.v[t]) * C + c] = __float2bfloat16(in[i]);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                 long long n) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n;
+       i += 1LL * gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+// ------------------------------------------------------------------ first layer (Cin = 3)
+// color_space_adjust (unet.py:22-23) + dropout (unet.py:29-30) + 3x3 im2col into 64 channels.
+struct ColorW {
+  float w[3][3];
+  float b[3];
+};
+__device__ __forceinline__ void color_adjust(const float* __restrict__ px, const ColorW& cw,
+                                             float (&o)[3]) {
+  const float a0 = px[0] - 0.5f, a1 = px[1] - 0.5f, a2 = px[2] - 0.5f;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) o[m] = a0 * cw.w[0][m] + a1 * cw.w[1][m] + a2 * cw.w[2][m] + cw.b[m];
+}
+
+__global__ void color_im2col_kernel(const float* __restrict__ img, int N, int S,
+                                    const float* __restrict__ w1, const float* __restrict__ b1,
+                                    int d, int oy, int ox, int Ho, int Wo,
+                                    __nv_bfloat16* __restrict__ out, float keep,
+                                    unsigned long long seed) {
+  ColorW cw;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) cw.w[i][j] = __ldg(w1 + i * 3 + j);
+    cw.b[i] = __ldg(b1 + i);
+  }
+  const long long total = 1LL * N * Ho * Wo;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % Wo);
+    const int y = static_cast<int>((i / Wo) % Ho);
+    const int n = static_cast<int>(i / (1LL * Wo * Ho));
+    float col[32];
+#pragma unroll
+    for (int j = 27; j < 32; ++j) col[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + oy + (t / 3) * d, xx = x + ox + (t % 3) * d;
+      const long long pix = (1LL * n * S + yy) * S + xx;
+      float o[3];
+      color_adjust(img + pix * 3, cw, o);
+      if (keep < 1.0f) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) o[m] *= keep_scale(seed, pix * 3 + m, keep);
+      }
+      col[t * 3 + 0] = o[0];
+      col[t * 3 + 1] = o[1];
+      col[t * 3 + 2] = o[2];
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 v;
+      v.x = pack_bf16x2(col[q * 8 + 0], col[q * 8 + 1]);
+      v.y = pack_bf16x2(col[q * 8 + 2], col[q * 8 + 3]);
+      v.z = pack_bf16x2(col[q * 8 + 4], col[q * 8 + 5]);
+      v.w = pack_bf16x2(col[q * 8 + 6], col[q * 8 + 7]);
+      op[q] = v;
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 4; q < 8; ++q) op[q] = z;
+  }
+}
+
+// d(color_space_adjust): gather d(net0) from d(im2col), then reduce dW1 = (img-0.5)^T d(net0).
+__global__ void color_im2col_bwd_kernel(const float* __restrict__ img, int N, int S,
+                                        const __nv_bfloat16* __restrict__ dcol, int d, int oy,
+                                        int ox, int Ho, int Wo, float* __restrict__ dw1,
+                                        float* __restrict__ db1, float keep,
+                                        unsigned long long seed) {
+  const int Hr = Ho + 2 * d, Wr = Wo + 2 * d;  // touched region of net0
+  const long long total = 1LL * N * Hr * Wr;
+  float acc[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const int rx = static_cast<int>(i % Wr);
+    const int ry = static_cast<int>((i / Wr) % Hr);
+    const int n = static_cast<int>(i / (1LL * Wr * Hr));
+    float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int y = ry - (t / 3) * d, x = rx - (t % 3) * d;
+      if (y >= 0 && y < Ho && x >= 0 && x < Wo) {
+        const __nv_bfloat16* p = dcol + ((1LL * n * Ho + y) * Wo + x) * 64 + t * 3;
+        g[0] += __bfloat162float(p[0]);
+        g[1] += __bfloat162float(p[1]);
+        g[2] += __bfloat162float(p[2]);
+      }
+    }
+    const long long pix = (1LL * n * S + ry + oy) * S + rx + ox;
+    if (keep < 1.0f) {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) g[m] *= keep_scale(seed, pix * 3 + m, keep);
+    }
+    const float* px = img + pix * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = px[c] - 0.5f;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) acc[c * 3 + m] += a * g[m];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) acc[9 + m] += g[m];
+  }
+  __shared__ float red[12];
+  if (threadIdx.x < 12) red[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[j], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) atomicAdd(dw1 + threadIdx.x, red[threadIdx.x]);
+  else if (threadIdx.x < 12) atomicAdd(db1 + threadIdx.x - 9, red[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------ pooling
+// tf.layers.max_pooling2d 2x2 / 2 (unet.py:52)
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ in, int N, int H, int W, int G,
+                                  uint4* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = 1LL * N * Ho * Wo * G;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    const long long p = i / G;
+    const int x = static_cast<int>(p % Wo);
+    const int y = static_cast<int>((p / Wo) % Ho);
+    const int n = static_cast<int>(p / (1LL * Wo * Ho));
+    const long long base = ((1LL * n * H + 2 * y) * W + 2 * x) * G + g;
+    float a[8], b[8];
+    unpack8(__ldg(in + base), a);
+    unpack8(__ldg(in + base + G), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], b[e]);
+    unpack8(__ldg(in + base + 1LL * W * G), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], b[e]);
+    unpack8(__ldg(in + base + 1LL * W * G + G), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], b[e]);
+    out[i] = pack8(a);
+  }
+}
+
+// MaxPoolGrad + crop-pad of the concat gradient + ReluGrad in one pass over the skip tensor
+// (unet.py:47-52, 70-85).  The pool gradient goes to the first maximum of each 2x2 window.
+__global__ void skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int W, int G,
+                                 const uint4* __restrict__ dP, const __nv_bfloat16* __restrict__ dC,
+                                 long long c_sn, long long c_sy, long long c_sx, int Hc, int Wc,
+                                 int crop_y, int crop_x, uint4* __restrict__ dZ) {
+  const long long total = 1LL * N * H * W * G;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    const long long p = i / G;
+    const int x = static_cast<int>(p % W);
+    const int y = static_cast<int>((p / W) % H);
+    const int n = static_cast<int>(p / (1LL * W * H));
+    float yv[8], gr[8];
+    unpack8(__ldg(Y + i), yv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gr[e] = 0.f;
+    if (dP != nullptr) {
+      const int wy = y & ~1, wx = x & ~1;
+      const int my = y & 1, mx = x & 1;
+      const int pos = my * 2 + mx;  // position of this element in row-major window order
+      const long long wbase = ((1LL * n * H + wy) * W + wx) * G + g;
+      float w[4][8];
+      unpack8(__ldg(Y + wbase), w[0]);
+      unpack8(__ldg(Y + wbase + G), w[1]);
+      unpack8(__ldg(Y + wbase + 1LL * W * G), w[2]);
+      unpack8(__ldg(Y + wbase + 1LL * W * G + G), w[3]);
+      float dp[8];
+      unpack8(__ldg(dP + ((1LL * n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * G + g), dp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int arg = 0;
+        float best = w[0][e];
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (w[q][e] > best) {
+            best = w[q][e];
+            arg = q;
+          }
+        if (arg == pos) gr[e] = dp[e];
+      }
+    }
+    if (dC != nullptr) {
+      const int cy = y - crop_y, cx = x - crop_x;
+      if (cy >= 0 && cy < Hc && cx >= 0 && cx < Wc) {
+        float dc[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dC + n * c_sn + cy * c_sy + cx * c_sx) + g),
+                dc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gr[e] += dc[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (!(yv[e] > 0.f)) gr[e] = 0.f;
+    dZ[i] = pack8(gr);
+  }
+}
+
+// ReluGrad on strided views: dZ (compact NHWC) = [Y > 0] * dY
+__global__ void relu_mask_kernel(const __nv_bfloat16* __restrict__ Y, long long y_sn,
+                                 long long y_sy, long long y_sx, const __nv_bfloat16* __restrict__ dY,
+                                 long long d_sn, long long d_sy, long long d_sx, int N, int H, int W,
+                                 int G, uint4* __restrict__ dZ) {
+  const long long total = 1LL * N * H * W * G;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    const long long p = i / G;
+    const int x = static_cast<int>(p % W);
+    const int y = static_cast<int>((p / W) % H);
+    const int n = static_cast<int>(p / (1LL * W * H));
+    float yv[8], dv[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(Y + n * y_sn + y * y_sy + x * y_sx) + g), yv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dY + n * d_sn + y * d_sy + x * d_sx) + g), dv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (!(yv[e] > 0.f)) dv[e] = 0.f;
+    dZ[i] = pack8(dv);
+  }
+}
+
+// BiasAddGrad: out[c] += sum over pixels.  blockDim = G * k threads; thread (lane, g).
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ v, long long sn, long long sy,
+                                 long long sx, int N, int H, int W, int G, int k,
+                                 float* __restrict__ out) {
+  extern __shared__ float sred[];  // [G*8]
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  for (int j = threadIdx.x; j < G * 8; j += blockDim.x) sred[j] = 0.f;
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const long long pixels = 1LL * N * H * W;
+  for (long long p = blockIdx.x * 1LL * k + lane; p < pixels; p += 1LL * gridDim.x * k) {
+    const int x = static_cast<int>(p % W);
+    const int y = static_cast<int>((p / W) % H);
+    const int n = static_cast<int>(p / (1LL * W * H));
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(v + n * sn + y * sy + x * sx) + g), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) atomicAdd(&sred[g * 8 + e], acc[e]);
+  __syncthreads();
+  for (int j = threadIdx.x; j < G * 8; j += blockDim.x) atomicAdd(out + j, sred[j]);
+}
+
+// ------------------------------------------------------------------ head
+// weight_output 1x1 conv (unet.py:95) + softmax P(road) (tf_aerial_images.py:147-148) + mean
+// sparse softmax cross-entropy (:103-110) and all gradients that leave this layer.
+// LP = C/8 lanes cooperate on one pixel (each owns 8 channels).
+template <int LP>
+__global__ void head_kernel(const uint4* __restrict__ act, long long pixels, const float* __restrict__ w,
+                            const float* __restrict__ b, const unsigned char* __restrict__ labels,
+                            float* __restrict__ probs, float* __restrict__ logits,
+                            float* __restrict__ loss, uint4* __restrict__ dZ, float* __restrict__ dW,
+                            float* __restrict__ db, float inv_count) {
+  constexpr int PPW = 32 / LP;  // pixels per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LP;  // channel group
+  const int pw = lane / LP;   // pixel slot in warp
+  float w0[8], w1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    w0[e] = __ldg(w + (sub * 8 + e) * 2 + 0);
+    w1[e] = __ldg(w + (sub * 8 + e) * 2 + 1);
+  }
+  const float b0 = __ldg(b), b1 = __ldg(b + 1);
+  float aw0[8], aw1[8], ab0 = 0.f, ab1 = 0.f, aloss = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) aw0[e] = aw1[e] = 0.f;
+
+  const long long warp_global = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (1LL * gridDim.x * blockDim.x) >> 5;
+  for (long long p0 = warp_global * PPW; p0 < pixels; p0 += n_warps * PPW) {
+    const long long p = p0 + pw;
+    const bool ok = p < pixels;
+    float a[8];
+    if (ok) unpack8(__ldg(act + p * LP + sub), a);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    }
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      l0 += a[e] * w0[e];
+      l1 += a[e] * w1[e];
+    }
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    }
+    l0 += b0;
+    l1 += b1;
+    const float mx = fmaxf(l0, l1);
+    const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx);
+    const float inv = 1.f / (e0 + e1);
+    const float p1 = e1 * inv;
+    if (ok && sub == 0) {
+      if (probs) probs[p] = p1;
+      if (logits) {
+        logits[p * 2] = l0;
+        logits[p * 2 + 1] = l1;
+      }
+    }
+    if (labels != nullptr && ok) {
+      const int lab = labels[p];
+      const float dl1 = (p1 - (lab ? 1.f : 0.f)) * inv_count;
+      const float dl0 = -dl1;  // (p0 - onehot0) = -(p1 - onehot1)
+      if (sub == 0) {
+        aloss += (mx + __logf(e0 + e1)) - (lab ? l1 : l0);
+        ab0 += dl0;
+        ab1 += dl1;
+      }
+      float gz[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        aw0[e] += a[e] * dl0;
+        aw1[e] += a[e] * dl1;
+        gz[e] = a[e] > 0.f ? dl0 * w0[e] + dl1 * w1[e] : 0.f;
+      }
+      dZ[p * LP + sub] = pack8(gz);
+    }
+  }
+  if (labels == nullptr) return;
+  // reduce across pixel slots of the warp, then across warps through shared memory
+  __shared__ float s_w[LP * 16];
+  __shared__ float s_s[3];
+  for (int j = threadIdx.x; j < LP * 16; j += blockDim.x) s_w[j] = 0.f;
+  if (threadIdx.x < 3) s_s[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int o = LP; o < 32; o <<= 1) {
+      aw0[e] += __shfl_xor_sync(0xffffffffu, aw0[e], o);
+      aw1[e] += __shfl_xor_sync(0xffffffffu, aw1[e], o);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    aloss += __shfl_xor_sync(0xffffffffu, aloss, o);
+    ab0 += __shfl_xor_sync(0xffffffffu, ab0, o);
+    ab1 += __shfl_xor_sync(0xffffffffu, ab1, o);
+  }
+  if (pw == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&s_w[(sub * 8 + e) * 2 + 0], aw0[e]);
+      atomicAdd(&s_w[(sub * 8 + e) * 2 + 1], aw1[e]);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&s_s[0], aloss);
+    atomicAdd(&s_s[1], ab0);
+    atomicAdd(&s_s[2], ab1);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < LP * 16; j += blockDim.x) atomicAdd(dW + j, s_w[j]);
+  if (threadIdx.x == 0) {
+    atomicAdd(loss, s_s[0] * inv_count);
+    atomicAdd(db, s_s[1]);
+    atomicAdd(db + 1, s_s[2]);
+  }
+}
+
+// ------------------------------------------------------------------ dropout / SGD
+// tf.nn.dropout (unet.py:30, 65): y = x / keep * floor(keep + U)
+__global__ void dropout_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n8,
+                               float keep, unsigned long long seed) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n8;
+       i += 1LL * gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(__ldg(x + i), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= keep_scale(seed, i * 8 + e, keep);
+    y[i] = pack8(f);
+  }
+}
+__global__ void dropout_mask_kernel(float* __restrict__ m, long long n, float keep,
+                                    unsigned long long seed) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n;
+       i += 1LL * gridDim.x * blockDim.x)
+    m[i] = keep_scale(seed, i, keep);
+}
+
+// tf.train.MomentumOptimizer, non-Nesterov (tf_aerial_images.py:116-121)
+__global__ void momentum_sgd_kernel(float4* __restrict__ w, float4* __restrict__ acc,
+                                    const float4* __restrict__ g, long long n4, float lr,
+                                    float momentum, float gscale) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n4;
+       i += 1LL * gridDim.x * blockDim.x) {
+    float4 a = acc[i], ww = w[i];
+    const float4 gg = __ldg(g + i);
+    a.x = momentum * a.x + gg.x * gscale;
+    a.y = momentum * a.y + gg.y * gscale;
+    a.z = momentum * a.z + gg.z * gscale;
+    a.w = momentum * a.w + gg.w * gscale;
+    ww.x -= lr * a.x;
+    ww.y -= lr * a.y;
+    ww.z -= lr * a.z;
+    ww.w -= lr * a.w;
+    acc[i] = a;
+    w[i] = ww;
+  }
+}
+__global__ void momentum_sgd_tail_kernel(float* w, float* acc, const float* g, long long begin,
+                                         long long n, float lr, float momentum, float gscale) {
+  const long long i = begin + blockIdx.x * 1LL * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float a = momentum * acc[i] + g[i] * gscale;
+    acc[i] = a;
+    w[i] -= lr * a;
+  }
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = 1LL * num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace rsu
+
+using namespace rsu;
+
+extern "C" {
+
+int rsu_pack_transpose(const float* in, void* out, int T, int R, int C, int ld, void* stream) {
+  if (T < 1 || R < 1 || C < 1) return set_error(RSU_EINVAL, "pack_transpose: empty");
+  if (ld == 0) ld = T * R;
+  if (ld < T * R) return set_error(RSU_EINVAL, "pack_transpose: ld %d < %d", ld, T * R);
+  dim3 grid((C + 31) / 32, (R + 31) / 32, T), block(32, 8);
+  pack_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      in, static_cast<__nv_bfloat16*>(out), T, R, C, ld);
+  return check_launch("pack_transpose");
+}
+
+int rsu_pack_permute(const float* in, void* out, int T, int R, int C, const int* perm_host,
+                     void* stream) {
+  if (T < 1 || T > 16 || R < 1 || C < 1) return set_error(RSU_EINVAL, "pack_permute: bad T=%d", T);
+  Perm perm;
+  for (int t = 0; t < 16; ++t) perm.v[t] = perm_host && t < T ? perm_host[t] : t;
+  const long long total = 1LL * T * R * C;
+  pack_permute_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      in, static_cast<__nv_bfloat16*>(out), T, R, C, perm);
+  return check_launch("pack_permute");
+}
+
+int rsu_cast_bf16(const float* in, void* out, long long n, void* stream) {
+  if (n < 1) return set_error(RSU_EINVAL, "cast: empty");
+  cast_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      in, static_cast<__nv_bfloat16*>(out), n);
+  return check_launch("cast_bf16");
+}
+
+int rsu_color_im2col(const float* img, int N, int S, const float* w1, const float* b1,
+                     int dilation, int oy, int ox, int Ho, int Wo, void* out, float keep,
+                     unsigned long long seed, void* stream) {
+  if (oy < 0 || ox < 0 || oy + Ho + 2 * dilation > S || ox + Wo + 2 * dilation > S)
+    return set_error(RSU_EINVAL, "color_im2col: window outside the %dx%d image", S, S);
+  if (reinterpret_cast<uintptr_t>(out) & 15) return set_error(RSU_EALIGN, "color_im2col: out");
+  const long long total = 1LL * N * Ho * Wo;
+  color_im2col_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(
+      img, N, S, w1, b1, dilation, oy, ox, Ho, Wo, static_cast<__nv_bfloat16*>(out), keep, seed);
+  return check_launch("color_im2col");
+}
+
+int rsu_color_im2col_bwd(const float* img, int N, int S, const void* dcol, int dilation, int oy,
+                         int ox, int Ho, int Wo, float* dw1, float* db1, float keep,
+                         unsigned long long seed, void* stream) {
+  if (oy < 0 || ox < 0 || oy + Ho + 2 * dilation > S || ox + Wo + 2 * dilation > S)
+    return set_error(RSU_EINVAL, "color_im2col_bwd: window outside the %dx%d image", S, S);
+  const long long total = 1LL * N * (Ho + 2 * dilation) * (Wo + 2 * dilation);
+  int grid = grid_for(total, 256);
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  color_im2col_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      img, N, S, static_cast<const __nv_bfloat16*>(dcol), dilation, oy, ox, Ho, Wo, dw1, db1, keep,
+      seed);
+  return check_launch("color_im2col_bwd");
+}
+
+int rsu_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, void* stream) {
+  if (H % 2 || W % 2 || C % 8) return set_error(RSU_EINVAL, "maxpool: H=%d W=%d C=%d", H, W, C);
+  const long long total = 1LL * N * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(in), N, H, W, C / 8, static_cast<uint4*>(out));
+  return check_launch("maxpool2x2");
+}
+
+int rsu_skip_grad(const void* Y, int N, int H, int W, int C, const void* dP, const rsu_view* dCrop,
+                  int crop_y, int crop_x, void* dZ, void* stream) {
+  if (C % 8) return set_error(RSU_EINVAL, "skip_grad: C=%d", C);
+  if (dP && (H % 2 || W % 2)) return set_error(RSU_EINVAL, "skip_grad: odd H/W with pool grad");
+  if (dCrop && (dCrop->C != C || dCrop->N != N || (dCrop->sx % 8) || (dCrop->sy % 8) ||
+                (dCrop->sn % 8) || (reinterpret_cast<uintptr_t>(dCrop->ptr) & 15)))
+    return set_error(RSU_EINVAL, "skip_grad: bad crop view");
+  const long long total = 1LL * N * H * W * (C / 8);
+  skip_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(Y), N, H, W, C / 8, static_cast<const uint4*>(dP),
+      dCrop ? static_cast<const __nv_bfloat16*>(dCrop->ptr) : nullptr, dCrop ? dCrop->sn : 0,
+      dCrop ? dCrop->sy : 0, dCrop ? dCrop->sx : 0, dCrop ? dCrop->H : 0, dCrop ? dCrop->W : 0,
+      crop_y, crop_x, static_cast<uint4*>(dZ));
+  return check_launch("skip_grad");
+}
+
+int rsu_relu_mask(const rsu_view* Y, const rsu_view* dY, void* dZ, void* stream) {
+  if (!Y || !dY || Y->C != dY->C || Y->H != dY->H || Y->W != dY->W || Y->N != dY->N || Y->C % 8)
+    return set_error(RSU_EINVAL, "relu_mask: view mismatch");
+  if ((Y->sx % 8) || (Y->sy % 8) || (Y->sn % 8) || (dY->sx % 8) || (dY->sy % 8) || (dY->sn % 8) ||
+      (reinterpret_cast<uintptr_t>(Y->ptr) & 15) || (reinterpret_cast<uintptr_t>(dY->ptr) & 15))
+    return set_error(RSU_EALIGN, "relu_mask: alignment");
+  const long long total = 1LL * Y->N * Y->H * Y->W * (Y->C / 8);
+  relu_mask_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(Y->ptr), Y->sn, Y->sy, Y->sx,
+      static_cast<const __nv_bfloat16*>(dY->ptr), dY->sn, dY->sy, dY->sx, Y->N, Y->H, Y->W,
+      Y->C / 8, static_cast<uint4*>(dZ));
+  return check_launch("relu_mask");
+}
+
+int rsu_bias_grad(const rsu_view* v, float* out, void* stream) {
+  if (!v || v->C % 8 || v->C / 8 > 1024) return set_error(RSU_EINVAL, "bias_grad: C");
+  if ((v->sx % 8) || (v->sy % 8) || (v->sn % 8) || (reinterpret_cast<uintptr_t>(v->ptr) & 15))
+    return set_error(RSU_EALIGN, "bias_grad: alignment");
+  const int G = v->C / 8;
+  int k = 256 / G;
+  if (k < 1) k = 1;
+  const long long pixels = 1LL * v->N * v->H * v->W;
+  long long blocks = (pixels + k - 1) / k;
+  const long long cap = 1LL * num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  bias_grad_kernel<<<static_cast<int>(blocks), G * k, G * 8 * sizeof(float), (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(v->ptr), v->sn, v->sy, v->sx, v->N, v->H, v->W, G, k, out);
+  return check_launch("bias_grad");
+}
+
+int rsu_head(const void* act, int N, int H, int W, int C, const float* w, const float* b,
+             const unsigned char* labels, float* probs, float* logits, float* loss, void* dZ,
+             float* dW, float* db, void* stream) {
+  const long long pixels = 1LL * N * H * W;
+  if (labels && (!loss || !dZ || !dW || !db))
+    return set_error(RSU_EINVAL, "head: training outputs missing");
+  const float inv_count = 1.0f / static_cast<float>(pixels);
+  const int threads = 256;
+  int grid = grid_for(pixels * (C / 8), threads);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+#define RSU_HEAD(LP)                                                                         \
+  head_kernel<LP><<<grid, threads, 0, (cudaStream_t)stream>>>(                               \
+      static_cast<const uint4*>(act), pixels, w, b, labels, probs, logits, loss,            \
+      static_cast<uint4*>(dZ), dW, db, inv_count)
+  if (C == 64) RSU_HEAD(8);
+  else if (C == 128) RSU_HEAD(16);
+  else if (C == 256) RSU_HEAD(32);
+  else return set_error(RSU_EINVAL, "head: C=%d unsupported (64/128/256)", C);
+#undef RSU_HEAD
+  return check_launch("head");
+}
+
+int rsu_dropout(const void* x, void* y, long long n, float keep, unsigned long long seed,
+                void* stream) {
+  if (n % 8) return set_error(RSU_EINVAL, "dropout: n %% 8");
+  if (!(keep > 0.f && keep <= 1.f)) return set_error(RSU_EINVAL, "dropout: keep=%f", keep);
+  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), n / 8, keep, seed);
+  return check_launch("dropout");
+}
+
+int rsu_dropout_mask(float* m, long long n, float keep, unsigned long long seed, void* stream) {
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(m, n, keep, seed);
+  return check_launch("dropout_mask");
+}
+
+int rsu_momentum_sgd(float* w, float* acc, const float* g, long long n, float lr, float momentum,
+                     float gscale, void* stream) {
+  if (n < 1) return set_error(RSU_EINVAL, "sgd: empty");
+  if ((reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(acc) & 15) ||
+      (reinterpret_cast<uintptr_t>(g) & 15))
+    return set_error(RSU_EALIGN, "sgd: pointers must be 16-byte aligned");
+  const long long n4 = n / 4;
+  if (n4 > 0) {
+    momentum_sgd_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(acc),
+        reinterpret_cast<const float4*>(g), n4, lr, momentum, gscale);
+    int rc = check_launch("momentum_sgd");
+    if (rc) return rc;
+  }
+  if (n4 * 4 < n) {
+    momentum_sgd_tail_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(w, acc, g, n4 * 4, n, lr, momentum,
+                                                                 gscale);
+    return check_launch("momentum_sgd_tail");
+  }
+  return RSU_OK;
+}
+
+}  // extern "C"

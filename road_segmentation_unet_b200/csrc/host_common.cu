@@ -1,0 +1,130 @@
+#include "host_common.h"
+
+#include <atomic>
+#include <mutex>
+#include <string.h>
+
+namespace rsu {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(RSU_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  count_launch();
+  return RSU_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_act_map(CUtensorMap* map, const rsu_view& v, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(RSU_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (v.C % 64 != 0) return set_error(RSU_EINVAL, "view channels %d not a multiple of 64", v.C);
+  if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) || (v.sx % 8) || (v.sy % 8) || (v.sn % 8))
+    return set_error(RSU_EALIGN, "view pointer/strides must be 16-byte aligned");
+  if (box_w < 1 || box_w > 256 || box_h < 1 || box_h > 256)
+    return set_error(RSU_EINVAL, "bad TMA box %dx%d", box_w, box_h);
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sn * 2};
+  // TMA wants non-degenerate strides even for extent-1 dims
+  if (v.N == 1 && strides[2] == 0) strides[2] = strides[1] * v.H;
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(RSU_ECUDA,
+                     "cuTensorMapEncodeTiled(act C=%d W=%d H=%d N=%d sx=%lld sy=%lld sn=%lld box "
+                     "%dx%d) -> %d",
+                     v.C, v.W, v.H, v.N, v.sx, v.sy, v.sn, box_w, box_h, (int)r);
+  return RSU_OK;
+}
+
+int encode_weight_map(CUtensorMap* map, const void* ptr, int K, int N, int box_n) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(RSU_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (K % 64 != 0) return set_error(RSU_EINVAL, "weight K %d not a multiple of 64", K);
+  if (reinterpret_cast<uintptr_t>(ptr) & 15)
+    return set_error(RSU_EALIGN, "weight pointer must be 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(RSU_ECUDA, "cuTensorMapEncodeTiled(weights K=%d N=%d box %d) -> %d", K, N,
+                     box_n, (int)r);
+  return RSU_OK;
+}
+
+void pick_tile(int W, int H, bool mult16, int* TW, int* TH) {
+  long best_tiles = -1;
+  int bw = 16, bh = 8;
+  for (int tw = 128; tw >= 4; --tw) {
+    for (int th = 128 / tw; th >= 1; --th) {
+      if (tw * th > 128) continue;
+      if (mult16 && (tw * th) % 16 != 0) continue;
+      if (tw < 8 && W >= 8) continue;  // keep contiguous runs >= 1 KiB
+      long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+      // fewer tiles first; then the smaller box (less padding work) is not a win because each
+      // tile costs a full 128-row MMA anyway, so prefer the wider tile for longer runs.
+      if (best_tiles < 0 || tiles < best_tiles) {
+        best_tiles = tiles;
+        bw = tw;
+        bh = th;
+      }
+    }
+  }
+  *TW = bw;
+  *TH = bh;
+}
+
+}  // namespace rsu
+
+extern "C" {
+const char* rsu_last_error(void) { return rsu::g_err; }
+int rsu_version(void) { return 100; }
+long long rsu_launch_count(void) { return rsu::g_launches.load(); }
+void rsu_reset_launch_count(void) { rsu::g_launches.store(0); }
+}

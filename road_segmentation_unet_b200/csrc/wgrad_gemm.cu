@@ -1,0 +1,295 @@
+// Weight-gradient GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   D[(tap, src, c), co] += sum over pixels of  X_src[pixel + tap + off, c] * G[pixel + goff, co]
+//
+// The reduction (GEMM K) dimension is the pixel index, which is the slow axis of both NHWC
+// operands, so both are consumed as MN-major: a TMA box {64 ch, TW, TH, 1} lands as TW*TH rows
+// of 128 B and is exactly the canonical "MN-major, SWIZZLE_128B" atom stack (8-row K groups
+// 1024 B apart).  One accumulator = 2 row atoms (128 weight rows: two (tap, 64-channel) blocks)
+// x BN gradient channels; 16 pixels are retired per tcgen05.mma.  Pixel tiles are divided among
+// `ksplit` CTAs whose partial sums are combined with fp32 atomics into the zero-initialised
+// output, which has TensorFlow's HWIO kernel layout [(tap, cin), cout].
+// Out-of-range pixels of either operand arrive as zeros from TMA and contribute nothing.
+//
+// Reference op replaced: Conv2DBackpropFilter of every tf.layers.conv2d / conv2d_transpose in
+// src/unet.py:34-45, 67, 88-91.
+#include "gemm_params.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace rsu {
+
+constexpr int kWgThreads = 256;
+constexpr int kBoxBytes = 16384;  // one 64-channel atom: up to 128 pixel rows of 128 B
+constexpr int kWgTmemCols = 512;
+constexpr int kWgAccStride = 256;
+
+struct AtomCoord {
+  int src, chunk, dy, dx;
+};
+
+__device__ __forceinline__ AtomCoord decode_atom(const WgradParams& p, int atom, int chunks_total) {
+  AtomCoord a;
+  const int tap = atom / chunks_total;
+  int cg = atom % chunks_total;
+  int s = 0;
+  while (s < p.n_src - 1 && cg >= p.src_chunks[s]) {
+    cg -= p.src_chunks[s];
+    ++s;
+  }
+  a.src = s;
+  a.chunk = cg;
+  a.dy = p.tap_dy[tap] + p.src_off_y[s];
+  a.dx = p.tap_dx[tap] + p.src_off_x[s];
+  return a;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+    wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_b_atoms = p.BN / 64;
+  const uint32_t stage_bytes = static_cast<uint32_t>(2 + n_b_atoms) * kBoxBytes;
+  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&p.a_map[s]);
+    tma_prefetch_desc(&p.b_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kWgTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  int chunks_total = 0;
+  for (int s = 0; s < p.n_src; ++s) chunks_total += p.src_chunks[s];
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int pix_tiles = p.n_img * tiles_per_img;
+  const int total_units = p.n_tiles_m * p.n_tiles_n * p.ksplit;
+  const int tile_pixels = p.TW * p.TH;
+  const uint32_t box_bytes = static_cast<uint32_t>(tile_pixels) * 128u;
+  const int mma_per_tile = tile_pixels / 16;
+
+  // unit -> (ks, n_tile, m_tile); m fastest so that concurrently running CTAs share the G tile
+  auto unit_range = [&](int unit, int* m_tile, int* n_tile, int* pt_begin, int* pt_end) {
+    *m_tile = unit % p.n_tiles_m;
+    const int rest = unit / p.n_tiles_m;
+    *n_tile = rest % p.n_tiles_n;
+    const int ks = rest / p.n_tiles_n;
+    *pt_begin = static_cast<int>(1LL * pix_tiles * ks / p.ksplit);
+    *pt_end = static_cast<int>(1LL * pix_tiles * (ks + 1) / p.ksplit);
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      int m_tile, n_tile, pt0, pt1;
+      unit_range(unit, &m_tile, &n_tile, &pt0, &pt1);
+      const int atom0 = m_tile * 2;
+      const int n_a = (atom0 + 1 < p.n_atoms) ? 2 : 1;
+      const AtomCoord a0 = decode_atom(p, atom0, chunks_total);
+      const AtomCoord a1 = decode_atom(p, n_a == 2 ? atom0 + 1 : atom0, chunks_total);
+      const int n0 = n_tile * p.BN;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        const int img = pt / tiles_per_img;
+        const int r = pt % tiles_per_img;
+        const int y0 = (r / p.tiles_x) * p.TH, x0 = (r % p.tiles_x) * p.TW;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t dst = smem_base + stage * stage_bytes;
+        mbar_expect_tx(full_bar(stage), static_cast<uint32_t>(n_a + n_b_atoms) * box_bytes);
+        tma_load_4d(dst, &p.a_map[a0.src], full_bar(stage), a0.chunk * 64, x0 + a0.dx, y0 + a0.dy,
+                    img);
+        if (n_a == 2)
+          tma_load_4d(dst + kBoxBytes, &p.a_map[a1.src], full_bar(stage), a1.chunk * 64,
+                      x0 + a1.dx, y0 + a1.dy, img);
+        for (int j = 0; j < n_b_atoms; ++j)
+          tma_load_4d(dst + (2 + j) * kBoxBytes, &p.b_map, full_bar(stage), n0 + j * 64,
+                      x0 + p.b_off_x, y0 + p.b_off_y, img);
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, true, true);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc_it = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++acc_it) {
+      int m_tile, n_tile, pt0, pt1;
+      unit_range(unit, &m_tile, &n_tile, &pt0, &pt1);
+      const uint32_t acc = acc_it & 1u;
+      const uint32_t acc_phase = (acc_it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kWgAccStride;
+      uint32_t first = 1;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * stage_bytes;
+        const uint32_t b_addr = a_addr + 2 * kBoxBytes;
+        for (int j = 0; j < mma_per_tile; ++j) {
+          // 16 pixels (K) per instruction = 16 rows of 128 B = 2 KiB further into every atom
+          const uint64_t adesc = make_smem_desc_sw128(a_addr + j * 2048, kBoxBytes, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr + j * 2048, kBoxBytes, 1024);
+          umma_bf16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tfull_bar(acc));
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: atomics to fp32
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    uint32_t acc_it = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++acc_it) {
+      int m_tile, n_tile, pt0, pt1;
+      unit_range(unit, &m_tile, &n_tile, &pt0, &pt1);
+      const uint32_t acc = acc_it & 1u;
+      const uint32_t acc_phase = (acc_it >> 1) & 1u;
+      const int atom = m_tile * 2 + (m >> 6);
+      const bool valid = atom < p.n_atoms && pt1 > pt0;
+      float* orow = p.out + (static_cast<long long>(atom) * 64 + (m & 63)) * p.ldo + n_tile * p.BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row =
+          tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kWgAccStride;
+      for (int ch = 0; ch < p.BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(t_row + ch * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(orow + ch * 32 + j, __uint_as_float(r[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kWgTmemCols);
+}
+
+}  // namespace rsu
+
+using namespace rsu;
+
+extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d) return set_error(RSU_EINVAL, "null descriptor");
+  if (d->n_src < 1 || d->n_src > kMaxSrc) return set_error(RSU_EINVAL, "n_src %d", d->n_src);
+  if (d->n_taps < 1 || d->n_taps > kMaxTaps) return set_error(RSU_EINVAL, "n_taps %d", d->n_taps);
+  if (d->grad.C % 64 != 0) return set_error(RSU_EINVAL, "grad channels %d % 64 != 0", d->grad.C);
+  if (d->H < 1 || d->W < 1 || d->N_img < 1) return set_error(RSU_EINVAL, "empty pixel grid");
+  if (reinterpret_cast<uintptr_t>(d->out) & 15)
+    return set_error(RSU_EALIGN, "wgrad output must be 16-byte aligned");
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int max_tw = d->W, max_th = d->H;
+  if (d->grad.W < max_tw) max_tw = d->grad.W;
+  if (d->grad.H < max_th) max_th = d->grad.H;
+  int chunks_total = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    if (d->src[s].W < max_tw) max_tw = d->src[s].W;
+    if (d->src[s].H < max_th) max_th = d->src[s].H;
+    chunks_total += d->src[s].C / 64;
+  }
+  int TW, TH;
+  pick_tile(max_tw, max_th, true, &TW, &TH);
+  if (TW > max_tw || TH > max_th || (TW * TH) % 16 != 0)
+    return set_error(RSU_EINVAL, "no valid pixel tile for %dx%d", d->W, d->H);
+  p.TW = TW;
+  p.TH = TH;
+  p.tiles_x = (d->W + TW - 1) / TW;
+  p.tiles_y = (d->H + TH - 1) / TH;
+  p.n_img = d->N_img;
+  p.n_src = d->n_src;
+  for (int s = 0; s < d->n_src; ++s) {
+    int rc = encode_act_map(&p.a_map[s], d->src[s], TW, TH);
+    if (rc) return rc;
+    p.src_chunks[s] = d->src[s].C / 64;
+    p.src_off_y[s] = d->src[s].off_y;
+    p.src_off_x[s] = d->src[s].off_x;
+  }
+  {
+    int rc = encode_act_map(&p.b_map, d->grad, TW, TH);
+    if (rc) return rc;
+  }
+  p.b_off_y = d->grad.off_y;
+  p.b_off_x = d->grad.off_x;
+  p.n_taps = d->n_taps;
+  for (int t = 0; t < d->n_taps; ++t) {
+    p.tap_dy[t] = d->tap_dy[t];
+    p.tap_dx[t] = d->tap_dx[t];
+  }
+  p.n_atoms = d->n_taps * chunks_total;
+  p.n_tiles_m = (p.n_atoms + 1) / 2;
+  const int cout = d->grad.C;
+  p.BN = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
+  p.n_tiles_n = cout / p.BN;
+  p.out = d->out;
+  p.ldo = d->ldo;
+
+  const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
+  const int mn_units = p.n_tiles_m * p.n_tiles_n;
+  int ksplit = (2 * num_sms() + mn_units - 1) / mn_units;
+  if (ksplit > pix_tiles) ksplit = pix_tiles;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+
+  const int stage_bytes = (2 + p.BN / 64) * kBoxBytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  const int smem = 1024 + stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RSU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long long total = 1LL * mn_units * ksplit;
+  int grid = num_sms();
+  if (total < grid) grid = static_cast<int>(total);
+  wgrad_gemm_kernel<<<grid, kWgThreads, smem, stream>>>(p, stages);
+  return check_launch("wgrad_gemm_kernel");
+}

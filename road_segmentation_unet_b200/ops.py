@@ -1,0 +1,205 @@
+"""Operator-level host wrappers over the C ABI (one function per TensorFlow op of the reference).
+
+Every function takes NHWC bf16 torch CUDA tensors purely as device buffers and launches
+hand-written sm_100a kernels from librsu_b200.so on the current stream.  Weight layouts:
+
+  HWIO fp32 master (TensorFlow's [kh, kw, Cin, Cout], what the optimizer updates)
+    -> forward pack   [Cout][tap][Cin]   bf16   (pack_conv_fwd)
+    -> dgrad pack     [Cin][tap][Cout]   bf16   (pack_conv_dgrad)
+  transpose-conv master [2, 2, Cout, Cin] (TensorFlow's conv2d_transpose kernel)
+    -> forward pack   [(a,b,co)][ci]     bf16   (cast only)
+    -> dgrad pack     [ci][(a,b,co)]     bf16   (transpose)
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvGemmDesc, View, WgradDesc, call, view
+
+
+def _taps(desc, taps):
+    desc.n_taps = len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        desc.tap_dy[i] = dy
+        desc.tap_dx[i] = dx
+
+
+def conv_taps(dilation=1, sign=1):
+    return [(sign * ky * dilation, sign * kx * dilation) for ky in range(3) for kx in range(3)]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None, accumulate=False,
+              shuffle_cout=0, grid_hw=None):
+    """Generic implicit GEMM (rsu_conv_gemm).  srcs: list of (tensor_or_View, off_y, off_x)."""
+    d = ConvGemmDesc()
+    d.n_src = len(srcs)
+    for i, (t, oy, ox) in enumerate(srcs):
+        v = t if isinstance(t, View) else view(t)
+        v.off_y, v.off_x = oy, ox
+        d.src[i] = v
+    _taps(d, taps)
+    d.weights = _ptr(weights)
+    d.Ntot = n_out
+    n, h, w, _ = out.shape
+    if grid_hw is None:
+        grid_hw = (h // 2, w // 2) if shuffle_cout else (h, w)
+    d.H_out, d.W_out, d.N_img = grid_hw[0], grid_hw[1], n
+    d.out = _ptr(out)
+    d.out_sn, d.out_sy, d.out_sx = out.stride()[:3]
+    d.shuffle_cout = shuffle_cout
+    d.bias = _ptr(bias)
+    d.relu = int(relu)
+    if mask is not None:
+        assert mask.shape == out.shape
+        d.mask = _ptr(mask)
+        d.mask_sn, d.mask_sy, d.mask_sx = mask.stride()[:3]
+    d.accumulate = int(accumulate)
+    call("rsu_conv_gemm", C.byref(d))
+
+
+def wgrad_gemm(srcs, taps, grad, grad_off, out, grid_hw):
+    """Generic weight-gradient GEMM (rsu_wgrad_gemm); out: fp32 [rows, Cout], pre-zeroed."""
+    d = WgradDesc()
+    d.n_src = len(srcs)
+    for i, (t, oy, ox) in enumerate(srcs):
+        v = t if isinstance(t, View) else view(t)
+        v.off_y, v.off_x = oy, ox
+        d.src[i] = v
+    _taps(d, taps)
+    g = grad if isinstance(grad, View) else view(grad)
+    g.off_y, g.off_x = grad_off
+    d.grad = g
+    d.H, d.W = grid_hw
+    d.N_img = g.N
+    d.out = _ptr(out)
+    d.ldo = out.stride(0)
+    call("rsu_wgrad_gemm", C.byref(d))
+
+
+# ------------------------------------------------------------------ weight packing
+def pack_conv_fwd(w_hwio, out, taps, cin, cout, ld=0):
+    """HWIO fp32 [taps, cin, cout] -> bf16 [cout][taps*cin] (row length ld)."""
+    call("rsu_pack_transpose", _ptr(w_hwio), _ptr(out), taps, cin, cout, ld)
+
+
+def pack_conv_dgrad(w_hwio, out, taps, cin, cout):
+    """HWIO fp32 [taps, cin, cout] -> bf16 [cin][taps][cout]."""
+    call("rsu_pack_permute", _ptr(w_hwio), _ptr(out), taps, cin, cout, None)
+
+
+def cast_bf16(src, out):
+    call("rsu_cast_bf16", _ptr(src), _ptr(out), src.numel())
+
+
+# ------------------------------------------------------------------ conv 3x3 (unet.py:34-45,88-91)
+def conv3x3_fwd(srcs, w_fwd, bias, out, dilation=1, relu=True):
+    """srcs: [(tensor, off_y, off_x)] in concat order; out [N,Ho,Wo,Cout] bf16."""
+    conv_gemm(srcs, conv_taps(dilation), w_fwd, out, out.shape[3], bias=bias, relu=relu)
+
+
+def conv3x3_dgrad(dz, w_dgrad, dx_window, dilation=1, mask=None, accumulate=False):
+    """dx_window[u,v] = sum_taps dz[u - ky*d, v - kx*d] W[ky,kx]^T over the touched input window
+    (extent = dz extent + 2*dilation); optional fused ReLU mask / accumulation."""
+    conv_gemm([(dz, 0, 0)], conv_taps(dilation, -1), w_dgrad, dx_window, dx_window.shape[3],
+              mask=mask, accumulate=accumulate)
+
+
+def conv3x3_wgrad(srcs, dz, dw, dilation=1):
+    """dw fp32 [9*Cin_total, Cout] (HWIO), pre-zeroed; srcs as in conv3x3_fwd."""
+    wgrad_gemm(srcs, conv_taps(dilation), dz, (0, 0), dw, (dz.shape[1], dz.shape[2]))
+
+
+# ------------------------------------------------------------------ conv2d_transpose (unet.py:67)
+def _quad_views(t):
+    """The four stride-2 phase views (a, b) of an NHWC tensor [N, 2H, 2W, C]."""
+    n, h2, w2, c = t.shape
+    sn, sy, sx, _ = t.stride()
+    out = []
+    for a in range(2):
+        for b in range(2):
+            out.append(View(C.c_void_p(t.data_ptr() + 2 * (a * sy + b * sx)), c, h2 // 2, w2 // 2,
+                            n, sn, 2 * sy, 2 * sx, 0, 0))
+    return out
+
+
+def upconv2x2_fwd(x, w_fwd, bias, out):
+    cout = out.shape[3]
+    conv_gemm([(x, 0, 0)], [(0, 0)], w_fwd, out, 4 * cout, bias=bias, shuffle_cout=cout)
+
+
+def upconv2x2_dgrad(dy, w_dgrad, dx, mask=None):
+    conv_gemm([(v, 0, 0) for v in _quad_views(dy)], [(0, 0)], w_dgrad, dx, dx.shape[3], mask=mask)
+
+
+def upconv2x2_wgrad(dy, x, dw):
+    """dw fp32 [4*Cout, Cin] (TensorFlow's [2,2,Cout,Cin]), pre-zeroed."""
+    wgrad_gemm([(v, 0, 0) for v in _quad_views(dy)], [(0, 0)], x, (0, 0), dw,
+               (x.shape[1], x.shape[2]))
+
+
+# ------------------------------------------------------------------ elementwise
+def maxpool2x2(x, out):
+    n, h, w, c = x.shape
+    call("rsu_maxpool2x2", _ptr(x), n, h, w, c, _ptr(out))
+
+
+def skip_grad(y, dpool, dcrop, crop_yx, dz):
+    n, h, w, c = y.shape
+    cv = None
+    if dcrop is not None:
+        cv = dcrop if isinstance(dcrop, View) else view(dcrop)
+    call("rsu_skip_grad", _ptr(y), n, h, w, c, _ptr(dpool), C.byref(cv) if cv is not None else None,
+         crop_yx[0], crop_yx[1], _ptr(dz))
+
+
+def relu_mask(y, dy, dz):
+    yv = y if isinstance(y, View) else view(y)
+    dv = dy if isinstance(dy, View) else view(dy)
+    call("rsu_relu_mask", C.byref(yv), C.byref(dv), _ptr(dz))
+
+
+def bias_grad(v, out):
+    vv = v if isinstance(v, View) else view(v)
+    call("rsu_bias_grad", C.byref(vv), _ptr(out))
+
+
+def head(act, w, b, labels=None, probs=None, logits=None, loss=None, dz=None, dw=None, db=None):
+    n, h, wd, c = act.shape
+    call("rsu_head", _ptr(act), n, h, wd, c, _ptr(w), _ptr(b), _ptr(labels), _ptr(probs),
+         _ptr(logits), _ptr(loss), _ptr(dz), _ptr(dw), _ptr(db))
+
+
+def dropout(x, y, keep, seed):
+    call("rsu_dropout", _ptr(x), _ptr(y), x.numel(), float(keep), int(seed))
+
+
+def dropout_mask(n, keep, seed, device="cuda"):
+    m = torch.empty(n, dtype=torch.float32, device=device)
+    call("rsu_dropout_mask", _ptr(m), n, float(keep), int(seed))
+    return m
+
+
+def momentum_sgd(w, acc, g, lr, momentum, gscale=1.0):
+    call("rsu_momentum_sgd", _ptr(w), _ptr(acc), _ptr(g), w.numel(), float(lr), float(momentum),
+         float(gscale))
+
+
+def color_im2col(img, w1, b1, dilation, oy, ox, out, keep=1.0, seed=0):
+    n, s = img.shape[0], img.shape[1]
+    call("rsu_color_im2col", _ptr(img), n, s, _ptr(w1), _ptr(b1), dilation, oy, ox, out.shape[1],
+         out.shape[2], _ptr(out), float(keep), int(seed))
+
+
+def color_im2col_bwd(img, dcol, dilation, oy, ox, dw1, db1, keep=1.0, seed=0):
+    n, s = img.shape[0], img.shape[1]
+    call("rsu_color_im2col_bwd", _ptr(img), n, s, _ptr(dcol), dilation, oy, ox, dcol.shape[1],
+         dcol.shape[2], _ptr(dw1), _ptr(db1), float(keep), int(seed))
+
+
+def launch_count():
+    return _lib.launch_count()

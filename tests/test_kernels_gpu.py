@@ -1,0 +1,341 @@
+"""Kernel-level parity: every CUDA entry point against the CPU oracle on seeded inputs.
+
+Tolerances: GEMM-class kernels 2e-2 relative (||a-b|| / ||b||, bf16 inputs with fp32 accumulate;
+the stated gate of BASELINE.json) -- in practice ~3e-3 because the oracle is fed the same
+bf16-rounded operands; data-movement kernels are bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def bf(x):
+    """Round an fp32 numpy array to bf16 precision (returned as fp32)."""
+    return torch.tensor(x, dtype=torch.float32).bfloat16().float().numpy()
+
+
+def dev(x, dtype=torch.bfloat16):
+    return torch.tensor(x, dtype=torch.float32).to("cuda").to(dtype).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from road_segmentation_unet_b200 import ops as _ops
+    return _ops
+
+
+def pack_fwd(ops, w_hwio):
+    kh, kw, cin, cout = w_hwio.shape
+    out = torch.zeros(cout, kh * kw * cin, dtype=torch.bfloat16, device="cuda")
+    ops.pack_conv_fwd(dev(w_hwio, torch.float32), out, kh * kw, cin, cout)
+    return out
+
+
+def pack_dgrad(ops, w_hwio):
+    kh, kw, cin, cout = w_hwio.shape
+    out = torch.zeros(cin, kh * kw * cout, dtype=torch.bfloat16, device="cuda")
+    ops.pack_conv_dgrad(dev(w_hwio, torch.float32), out, kh * kw, cin, cout)
+    return out
+
+
+CONV_CASES = [
+    # (N, H, Cin, Cout, dilation)
+    (1, 18, 64, 64, 1),     # single tile row set, one N tile of 64
+    (2, 40, 64, 128, 1),    # BN = 128
+    (1, 37, 128, 256, 1),   # ragged edges, BN = 256, 2 K chunks per tap
+    (2, 30, 64, 512, 2),    # dilation 2, two N tiles
+    (3, 12, 256, 64, 1),    # tiny spatial, deep K
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_fwd(ops, case):
+    n, h, cin, cout, d = case
+    rs = np.random.RandomState(1)
+    x = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    w = bf((rs.randn(3, 3, cin, cout) / np.sqrt(9 * cin)).astype(np.float32))
+    b = rs.randn(cout).astype(np.float32)
+    ho = h - 2 * d
+    out = torch.full((n, ho, ho, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3_fwd([(dev(x), 0, 0)], pack_fwd(ops, w), dev(b, torch.float32), out, dilation=d)
+    ref = torch.relu(O.conv2d_valid(torch.tensor(x), torch.tensor(w), torch.tensor(b), d)).numpy()
+    err = rel_err(out.float().cpu().numpy(), ref)
+    assert err < 2e-2, err
+    assert err < 6e-3, err  # same bf16 operands: only the output rounding is left
+
+
+def test_conv3x3_fwd_concat_crop(ops):
+    """Fused crop + concat: three sources with different extents and crop offsets (unet.py:70-85)."""
+    rs = np.random.RandomState(2)
+    n, t = 2, 20
+    skip = bf(rs.randn(n, 28, 28, 128).astype(np.float32))
+    dil = bf(rs.randn(n, 24, 24, 128).astype(np.float32))
+    up = bf(rs.randn(n, t, t, 64).astype(np.float32))
+    w = bf((rs.randn(3, 3, 320, 128) / np.sqrt(9 * 320)).astype(np.float32))
+    b = rs.randn(128).astype(np.float32)
+    out = torch.zeros(n, t - 2, t - 2, 128, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3_fwd([(dev(skip), 4, 4), (dev(dil), 2, 2), (dev(up), 0, 0)], pack_fwd(ops, w),
+                    dev(b, torch.float32), out)
+    cat = torch.cat([O.center_crop(torch.tensor(skip), t), O.center_crop(torch.tensor(dil), t),
+                     torch.tensor(up)], dim=3)
+    ref = torch.relu(O.conv2d_valid(cat, torch.tensor(w), torch.tensor(b))).numpy()
+    assert rel_err(out.float().cpu().numpy(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("case", [(2, 22, 64, 64, 1), (1, 27, 128, 256, 2), (2, 16, 256, 128, 1)])
+def test_conv3x3_dgrad(ops, case):
+    """Conv2DBackpropInput with the fused ReluGrad mask, checked against autograd of the oracle."""
+    n, h, cin, cout, d = case
+    rs = np.random.RandomState(3)
+    x = torch.tensor(bf(rs.randn(n, h, h, cin).astype(np.float32)), requires_grad=True)
+    w = bf((rs.randn(3, 3, cin, cout) / np.sqrt(9 * cin)).astype(np.float32))
+    ho = h - 2 * d
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    y = O.conv2d_valid(x, torch.tensor(w), None, d)
+    y.backward(torch.tensor(dz))
+    mask_src = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    ref = x.grad.numpy() * (mask_src > 0)
+    out = torch.zeros(n, h, h, cin, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3_dgrad(dev(dz), pack_dgrad(ops, w), out, dilation=d, mask=dev(mask_src))
+    assert rel_err(out.float().cpu().numpy(), ref) < 6e-3
+    # accumulate into a window of a larger tensor
+    big = torch.ones(n, h + 6, h + 6, cin, dtype=torch.bfloat16, device="cuda")
+    win = big[:, 2:2 + h, 4:4 + h, :]
+    ops.conv3x3_dgrad(dev(dz), pack_dgrad(ops, w), win, dilation=d, accumulate=True)
+    ref2 = np.ones((n, h + 6, h + 6, cin), dtype=np.float32)
+    ref2[:, 2:2 + h, 4:4 + h, :] += x.grad.numpy()
+    assert rel_err(big.float().cpu().numpy(), ref2) < 8e-3
+
+
+@pytest.mark.parametrize("case", [(2, 20, 64, 64, 1), (1, 35, 128, 64, 1), (2, 24, 64, 256, 2),
+                                  (4, 16, 256, 512, 1)])
+def test_conv3x3_wgrad(ops, case):
+    n, h, cin, cout, d = case
+    rs = np.random.RandomState(4)
+    x = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    ho = h - 2 * d
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    w = torch.zeros(3, 3, cin, cout, requires_grad=True)
+    y = O.conv2d_valid(torch.tensor(x), w, None, d)
+    y.backward(torch.tensor(dz))
+    ref = w.grad.numpy().reshape(9 * cin, cout)
+    out = torch.zeros(9 * cin, cout, dtype=torch.float32, device="cuda")
+    ops.conv3x3_wgrad([(dev(x), 0, 0)], dev(dz), out, dilation=d)
+    assert rel_err(out.cpu().numpy(), ref) < 2e-3
+
+
+def test_conv3x3_wgrad_concat(ops):
+    rs = np.random.RandomState(5)
+    n, t = 2, 18
+    skip = bf(rs.randn(n, 26, 26, 128).astype(np.float32))
+    up = bf(rs.randn(n, t, t, 64).astype(np.float32))
+    dz = bf(rs.randn(n, t - 2, t - 2, 64).astype(np.float32))
+    w = torch.zeros(3, 3, 192, 64, requires_grad=True)
+    cat = torch.cat([O.center_crop(torch.tensor(skip), t), torch.tensor(up)], dim=3)
+    O.conv2d_valid(cat, w, None).backward(torch.tensor(dz))
+    out = torch.zeros(9 * 192, 64, dtype=torch.float32, device="cuda")
+    ops.conv3x3_wgrad([(dev(skip), 4, 4), (dev(up), 0, 0)], dev(dz), out)
+    assert rel_err(out.cpu().numpy(), w.grad.numpy().reshape(9 * 192, 64)) < 2e-3
+
+
+@pytest.mark.parametrize("case", [(2, 9, 128, 64), (1, 14, 256, 128), (3, 6, 512, 256)])
+def test_upconv2x2(ops, case):
+    n, h, cin, cout = case
+    rs = np.random.RandomState(6)
+    x = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    w = bf((rs.randn(2, 2, cout, cin) / np.sqrt(cin)).astype(np.float32))
+    b = rs.randn(cout).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True)
+    wt = torch.tensor(w, requires_grad=True)
+    y = O.conv2d_transpose_2x2(xt, wt, torch.tensor(b))
+    # forward
+    w_fwd = torch.zeros(4 * cout, cin, dtype=torch.bfloat16, device="cuda")
+    ops.cast_bf16(dev(w, torch.float32), w_fwd)
+    out = torch.zeros(n, 2 * h, 2 * h, cout, dtype=torch.bfloat16, device="cuda")
+    ops.upconv2x2_fwd(dev(x), w_fwd, dev(b, torch.float32), out)
+    assert rel_err(out.float().cpu().numpy(), y.detach().numpy()) < 6e-3
+    # gradients; dy is a channel slice of a wider "concat gradient" tensor
+    dy = bf(rs.randn(n, 2 * h, 2 * h, cout).astype(np.float32))
+    y.backward(torch.tensor(dy))
+    wide = torch.zeros(n, 2 * h, 2 * h, 3 * cout, dtype=torch.bfloat16, device="cuda")
+    wide[..., 2 * cout:] = dev(dy)
+    dy_view = wide[..., 2 * cout:]
+    w_dg = torch.zeros(cin, 4 * cout, dtype=torch.bfloat16, device="cuda")
+    ops.pack_conv_fwd(dev(w, torch.float32), w_dg, 1, 4 * cout, cin)
+    dx = torch.zeros(n, h, h, cin, dtype=torch.bfloat16, device="cuda")
+    ops.upconv2x2_dgrad(dy_view, w_dg, dx)
+    assert rel_err(dx.float().cpu().numpy(), xt.grad.numpy()) < 6e-3
+    dw = torch.zeros(4 * cout, cin, dtype=torch.float32, device="cuda")
+    ops.upconv2x2_wgrad(dy_view, dev(x), dw)
+    assert rel_err(dw.cpu().numpy(), wt.grad.numpy().reshape(4 * cout, cin)) < 2e-3
+
+
+def test_maxpool_and_skip_grad(ops):
+    rs = np.random.RandomState(7)
+    n, h, c, t = 2, 12, 64, 8
+    y = bf(np.maximum(rs.randn(n, h, h, c), 0).astype(np.float32))
+    yt = torch.tensor(y, requires_grad=True)
+    p = O.max_pool_2x2(yt)
+    out = torch.zeros(n, h // 2, h // 2, c, dtype=torch.bfloat16, device="cuda")
+    ops.maxpool2x2(dev(y), out)
+    assert np.array_equal(out.float().cpu().numpy(), p.detach().numpy())
+    dp = bf(rs.randn(n, h // 2, h // 2, c).astype(np.float32))
+    dcat = bf(rs.randn(n, t, t, 3 * c).astype(np.float32))
+    crop = O.center_crop(yt, t)
+    (p * torch.tensor(dp)).sum().backward(retain_graph=True)
+    (crop * torch.tensor(dcat[..., :c])).sum().backward()
+    ref = yt.grad.numpy() * (y > 0)
+    dz = torch.zeros(n, h, h, c, dtype=torch.bfloat16, device="cuda")
+    dcat_d = dev(dcat)
+    ops.skip_grad(dev(y), dev(dp), dcat_d[..., :c], (2, 2), dz)
+    got = dz.float().cpu().numpy()
+    # ties inside a pooling window (equal positive bf16 values) may route the gradient to a
+    # different element than the fp32 oracle; compare where windows have a unique maximum
+    win = y.reshape(n, h // 2, 2, h // 2, 2, c)
+    mx = win.max(axis=(2, 4), keepdims=True)
+    unique = ((win == mx).sum(axis=(2, 4), keepdims=True) == 1)
+    unique = np.broadcast_to(unique, win.shape).reshape(n, h, h, c)
+    assert rel_err(got[unique], bf(ref)[unique]) < 1e-2
+    assert unique.mean() > 0.5
+
+
+def test_relu_mask_and_bias_grad(ops):
+    rs = np.random.RandomState(8)
+    n, h, c = 2, 11, 128
+    y = bf(rs.randn(n, h, h, c).astype(np.float32))
+    wide = bf(rs.randn(n, h, h, 3 * c).astype(np.float32))
+    wide_d = dev(wide)
+    dz = torch.zeros(n, h, h, c, dtype=torch.bfloat16, device="cuda")
+    ops.relu_mask(dev(y), wide_d[..., c:2 * c], dz)
+    ref = wide[..., c:2 * c] * (y > 0)
+    assert np.array_equal(dz.float().cpu().numpy(), ref)
+    db = torch.zeros(c, dtype=torch.float32, device="cuda")
+    ops.bias_grad(dz, db)
+    assert rel_err(db.cpu().numpy(), ref.sum(axis=(0, 1, 2))) < 1e-5
+    db2 = torch.zeros(c, dtype=torch.float32, device="cuda")
+    ops.bias_grad(wide_d[..., 2 * c:], db2)
+    assert rel_err(db2.cpu().numpy(), wide[..., 2 * c:].sum(axis=(0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("c", [64, 128])
+def test_head(ops, c):
+    rs = np.random.RandomState(9)
+    n, h = 2, 13
+    act = bf(np.maximum(rs.randn(n, h, h, c), 0).astype(np.float32))
+    w = (rs.randn(c, 2) / 8).astype(np.float32)
+    b = rs.randn(2).astype(np.float32)
+    labels = (rs.rand(n, h, h) < 0.3).astype(np.uint8)
+    at = torch.tensor(act, requires_grad=True)
+    wt = torch.tensor(w.reshape(1, 1, c, 2), requires_grad=True)
+    bt = torch.tensor(b, requires_grad=True)
+    logits = O.conv2d_valid(at, wt, bt)
+    loss, probs = O.loss_and_probs(logits, torch.tensor(labels))
+    loss.backward()
+    d_probs = torch.zeros(n, h, h, dtype=torch.float32, device="cuda")
+    d_logits = torch.zeros(n, h, h, 2, dtype=torch.float32, device="cuda")
+    d_loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+    d_dz = torch.zeros(n, h, h, c, dtype=torch.bfloat16, device="cuda")
+    d_dw = torch.zeros(c, 2, dtype=torch.float32, device="cuda")
+    d_db = torch.zeros(2, dtype=torch.float32, device="cuda")
+    ops.head(dev(act), dev(w, torch.float32), dev(b, torch.float32),
+             torch.tensor(labels).cuda(), d_probs, d_logits, d_loss, d_dz, d_dw, d_db)
+    assert rel_err(d_logits.cpu().numpy(), logits.detach().numpy()) < 1e-5
+    assert rel_err(d_probs.cpu().numpy(), probs.detach().numpy()) < 1e-5
+    assert abs(d_loss.item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
+    assert rel_err(d_dw.cpu().numpy(), wt.grad.numpy().reshape(c, 2)) < 1e-4
+    assert rel_err(d_db.cpu().numpy(), bt.grad.numpy()) < 1e-4
+    assert rel_err(d_dz.float().cpu().numpy(), at.grad.numpy() * (act > 0)) < 6e-3
+    # predict-only mode
+    p2 = torch.zeros(n, h, h, dtype=torch.float32, device="cuda")
+    ops.head(dev(act), dev(w, torch.float32), dev(b, torch.float32), probs=p2)
+    assert torch.equal(p2, d_probs)
+
+
+def test_momentum_sgd_and_dropout(ops):
+    rs = np.random.RandomState(10)
+    n = 1003
+    w, a, g = (rs.randn(n).astype(np.float32) for _ in range(3))
+    dw, da, dg = (dev(v, torch.float32) for v in (w, a, g))
+    ops.momentum_sgd(dw, da, dg, 0.01, 0.9)
+    acc = 0.9 * a + g
+    assert np.allclose(da.cpu().numpy(), acc, rtol=1e-6, atol=1e-7)
+    assert np.allclose(dw.cpu().numpy(), w - 0.01 * acc, rtol=1e-6, atol=1e-7)
+    x = bf(rs.randn(4096).astype(np.float32))
+    y = torch.zeros(4096, dtype=torch.bfloat16, device="cuda")
+    ops.dropout(dev(x), y, 0.8, 42)
+    m = ops.dropout_mask(4096, 0.8, 42).cpu().numpy()
+    assert set(np.unique(m)).issubset({0.0, np.float32(1 / 0.8)})
+    assert 0.7 < (m > 0).mean() < 0.9
+    assert np.array_equal(y.float().cpu().numpy(), bf(x * m))
+
+
+@pytest.mark.parametrize("case", [(1, 1, 0.0), (2, 2, 0.8)])
+def test_color_im2col(ops, case):
+    """color_space_adjust + dropout + 3x3 im2col and its weight gradient (unet.py:22-30)."""
+    d, n, keep_arg = case
+    keep = keep_arg if keep_arg > 0 else 1.0
+    rs = np.random.RandomState(11)
+    s, oy, ox = 20, 3, 1
+    ho = wo = 10
+    img = rs.rand(n, s, s, 3).astype(np.float32)
+    w1 = rs.randn(3, 3).astype(np.float32)
+    b1 = rs.randn(3).astype(np.float32)
+    seed = 77
+    scales = np.ones(n * s * s * 3, dtype=np.float32)
+    if keep < 1.0:
+        scales = ops.dropout_mask(n * s * s * 3, keep, seed).cpu().numpy()
+    scales = scales.reshape(n, s, s, 3)
+    net0 = ((img - 0.5) @ w1 + b1) * scales
+    col = np.zeros((n, ho, wo, 64), dtype=np.float32)
+    for t in range(9):
+        ky, kx = divmod(t, 3)
+        col[..., t * 3:t * 3 + 3] = net0[:, oy + ky * d:oy + ky * d + ho, ox + kx * d:ox + kx * d + wo]
+    out = torch.full((n, ho, wo, 64), 3.0, dtype=torch.bfloat16, device="cuda")
+    d_img = dev(img, torch.float32)
+    ops.color_im2col(d_img, dev(w1, torch.float32), dev(b1, torch.float32), d, oy, ox, out, keep, seed)
+    assert rel_err(out.float().cpu().numpy(), bf(col)) < 1e-6 + 4e-3
+    assert np.abs(out.float().cpu().numpy()[..., 27:]).max() == 0
+    # backward: dW1, db1 from d(col)
+    dcol = bf(rs.randn(n, ho, wo, 64).astype(np.float32))
+    dnet = np.zeros((n, s, s, 3), dtype=np.float64)
+    for t in range(9):
+        ky, kx = divmod(t, 3)
+        dnet[:, oy + ky * d:oy + ky * d + ho, ox + kx * d:ox + kx * d + wo] += dcol[..., t * 3:t * 3 + 3]
+    dnet *= scales
+    ref_dw = np.einsum("nhwc,nhwm->cm", (img - 0.5).astype(np.float64), dnet)
+    ref_db = dnet.sum(axis=(0, 1, 2))
+    dw = torch.zeros(3, 3, dtype=torch.float32, device="cuda")
+    db = torch.zeros(3, dtype=torch.float32, device="cuda")
+    ops.color_im2col_bwd(d_img, dev(dcol), d, oy, ox, dw, db, keep, seed)
+    assert rel_err(dw.cpu().numpy(), ref_dw) < 1e-4
+    assert rel_err(db.cpu().numpy(), ref_db) < 1e-4
+
+
+def test_first_layer_via_im2col(ops):
+    """Cin = 3 convolution as im2col(64) x padded weights on the tensor cores."""
+    rs = np.random.RandomState(12)
+    n, s, cout = 2, 30, 64
+    img = rs.rand(n, s, s, 3).astype(np.float32)
+    w1 = np.eye(3, dtype=np.float32)
+    b1 = np.zeros(3, dtype=np.float32)
+    w = bf((rs.randn(3, 3, 3, cout) / np.sqrt(27)).astype(np.float32))
+    b = rs.randn(cout).astype(np.float32)
+    ho = s - 2
+    col = torch.zeros(n, ho, ho, 64, dtype=torch.bfloat16, device="cuda")
+    ops.color_im2col(dev(img, torch.float32), dev(w1, torch.float32), dev(b1, torch.float32), 1, 0, 0, col)
+    wp = torch.zeros(cout, 64, dtype=torch.bfloat16, device="cuda")
+    ops.pack_conv_fwd(dev(w, torch.float32), wp, 1, 27, cout, ld=64)
+    out = torch.zeros(n, ho, ho, cout, dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([(col, 0, 0)], [(0, 0)], wp, out, cout, bias=dev(b, torch.float32), relu=True)
+    ref = torch.relu(O.conv2d_valid(torch.tensor(bf(img - 0.5)), torch.tensor(w), torch.tensor(b))).numpy()
+    assert rel_err(out.float().cpu().numpy(), ref) < 6e-3

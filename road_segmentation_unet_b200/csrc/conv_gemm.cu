@@ -290,11 +290,8 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
   }
   ktot *= d->n_taps;
   int TW, TH;
-  pick_tile(max_tw < d->W_out ? max_tw : d->W_out, max_th < d->H_out ? max_th : d->H_out, false,
-            &TW, &TH);
-  // pick_tile minimises tiles over the clamped extent; recompute the grid over the real output
-  if (TW > max_tw) TW = max_tw;
-  if (TH > max_th) TH = max_th;
+  pick_tile(d->W_out, d->H_out, max_tw, max_th, false, &TW, &TH);
+  if (TW < 1 || TH < 1) return set_error(RSU_EINVAL, "no valid tile for %dx%d", d->W_out, d->H_out);
   p.TW = TW;
   p.TH = TH;
   p.tiles_x = (d->W_out + TW - 1) / TW;

@@ -135,8 +135,8 @@ __global__ void overlap_average_kernel(const float* __restrict__ patches, int N,
 
 // crop_imgs(rotate_imgs(x, angle), crop) (images.py:313-373).  scipy.ndimage.rotate with
 // order=0, reshape=True, mode='constant', cval=0: output pixel o maps to input coordinate
-// R*o + offset (fp64); the sample is in[floor(y+0.5), floor(x+0.5)] when that index is inside
-// the image, else 0.  Only the centre crop is ever materialised.
+// R*o + offset (fp64); the sample is in[floor(y+0.5), floor(x+0.5)] when the unrounded
+// coordinate lies in [0, H-1] on both axes, else 0.  Only the centre crop is ever materialised.
 struct RotParams {
   double m00, m01, m10, m11, off0, off1;
   int out_side, crop0;
@@ -157,7 +157,10 @@ __global__ void rotate_nn_crop_kernel(const float* __restrict__ in, int N, int H
     const long long ry = static_cast<long long>(floor(iy + 0.5));
     const long long rx = static_cast<long long>(floor(ix + 0.5));
     float v = 0.f;
-    if (ry >= 0 && ry < H && rx >= 0 && rx < H) v = __ldg(in + ((1LL * n * H + ry) * H + rx) * C + c);
+    // mode='constant' is decided on the unrounded coordinate: outside [0, H-1] -> cval
+    const double hi = static_cast<double>(H - 1);
+    if (iy >= 0.0 && iy <= hi && ix >= 0.0 && ix <= hi)
+      v = __ldg(in + ((1LL * n * H + ry) * H + rx) * C + c);
     out[i] = v;
   }
 }

@@ -98,17 +98,18 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, int K, int N, int box_n
   return RSU_OK;
 }
 
-void pick_tile(int W, int H, bool mult16, int* TW, int* TH) {
+void pick_tile(int W, int H, int max_tw, int max_th, bool mult16, int* TW, int* TH) {
   long best_tiles = -1;
-  int bw = 16, bh = 8;
-  for (int tw = 128; tw >= 4; --tw) {
-    for (int th = 128 / tw; th >= 1; --th) {
-      if (tw * th > 128) continue;
+  int bw = 0, bh = 0;
+  if (max_tw > 128) max_tw = 128;
+  for (int tw = max_tw; tw >= 1; --tw) {
+    if (tw < 8 && max_tw >= 8) break;  // keep contiguous runs >= 1 KiB when possible
+    int th_max = 128 / tw;
+    if (th_max > max_th) th_max = max_th;
+    for (int th = th_max; th >= 1; --th) {
       if (mult16 && (tw * th) % 16 != 0) continue;
-      if (tw < 8 && W >= 8) continue;  // keep contiguous runs >= 1 KiB
-      long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
-      // fewer tiles first; then the smaller box (less padding work) is not a win because each
-      // tile costs a full 128-row MMA anyway, so prefer the wider tile for longer runs.
+      const long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+      // fewest tiles wins (every tile costs a full 128-row MMA); ties keep the wider tile
       if (best_tiles < 0 || tiles < best_tiles) {
         best_tiles = tiles;
         bw = tw;
@@ -116,7 +117,7 @@ void pick_tile(int W, int H, bool mult16, int* TW, int* TH) {
       }
     }
   }
-  *TW = bw;
+  *TW = bw;  // 0 x 0 when no admissible tile exists
   *TH = bh;
 }
 

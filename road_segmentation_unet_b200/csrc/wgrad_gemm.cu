@@ -234,9 +234,9 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
     chunks_total += d->src[s].C / 64;
   }
   int TW, TH;
-  pick_tile(max_tw, max_th, true, &TW, &TH);
-  if (TW > max_tw || TH > max_th || (TW * TH) % 16 != 0)
-    return set_error(RSU_EINVAL, "no valid pixel tile for %dx%d", d->W, d->H);
+  pick_tile(d->W, d->H, max_tw, max_th, true, &TW, &TH);
+  if (TW < 1 || TH < 1 || (TW * TH) % 16 != 0)
+    return set_error(RSU_EINVAL, "no valid pixel tile for %dx%d (need TW*TH %% 16 == 0)", d->W, d->H);
   p.TW = TW;
   p.TH = TH;
   p.tiles_x = (d->W + TW - 1) / TW;

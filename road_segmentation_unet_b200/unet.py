@@ -1,0 +1,532 @@
+"""U-Net model builder -- host-side mirror of the reference's src/unet.py.
+
+`forward(X, num_layers, root_size, dilated_layers, dropout_keep=None)` and
+`input_size_needed(output_size, num_layers)` keep the reference signatures (src/unet.py:12, :100).
+Instead of a TensorFlow graph, `forward` plans a `UNet` engine: a static schedule of hand-written
+sm_100a kernels (librsu_b200.so) over preallocated NHWC bf16 buffers, with fp32 master weights
+stored under TensorFlow's variable names and layouts.
+
+Layer map (src/unet.py line -> kernel):
+  :22-23  color_space_adjust   -> rsu_color_im2col (fused with the Cin = 3 im2col)
+  :29-30  dropout              -> fused into rsu_color_im2col / rsu_dropout
+  :34-39  dilated 3x3 pair     -> rsu_conv_gemm, tap stride 2, only the window the decoder crops
+  :42-45  3x3 conv + ReLU      -> rsu_conv_gemm (tcgen05 implicit GEMM, bias + ReLU epilogue)
+  :52     2x2 max pool         -> rsu_maxpool2x2
+  :67-68  conv2d_transpose     -> rsu_conv_gemm with pixel-shuffle epilogue
+  :70-85  crop + concat        -> never materialised: the consumer's K loop walks 2-3 sources
+  :95     weight_output + loss -> rsu_head (1x1 conv + softmax + CE + gradients)
+The deepest dilated pair and the last pool are dead code in the reference (:56-59): their weights
+exist (checkpoint parity) but are never evaluated.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def input_size_needed(output_size, num_layers):
+    """Utility function to compute image size for a given U-Net output (src/unet.py:100-115)."""
+    for i in range(num_layers - 1):
+        assert output_size % 2 == 0, 'expand layer {} has size {} not divisible by 2' \
+            .format(num_layers - i, output_size)
+        output_size = (output_size + 4) / 2
+
+    for i in range(num_layers - 1):
+        output_size = (output_size + 4) * 2
+
+    return int(output_size + 4)
+
+
+def variable_shapes(num_layers, root_size, dilated_layers):
+    """TensorFlow variables of src/unet.py:23-95 in creation order: name -> shape."""
+    shapes = OrderedDict()
+    shapes["color_space_adjust/kernel"] = (1, 1, 3, 3)
+    shapes["color_space_adjust/bias"] = (3,)
+    cin, f = 3, root_size
+    for i in range(num_layers):
+        if dilated_layers:
+            shapes["conv_dilut_%d/atrous_conv1/kernel" % i] = (3, 3, cin, f)
+            shapes["conv_dilut_%d/atrous_conv1/bias" % i] = (f,)
+            shapes["conv_dilut_%d/atrous_conv2/kernel" % i] = (3, 3, f, f)
+            shapes["conv_dilut_%d/atrous_conv2/bias" % i] = (f,)
+        shapes["conv_%d/conv1/kernel" % i] = (3, 3, cin, f)
+        shapes["conv_%d/conv1/bias" % i] = (f,)
+        shapes["conv_%d/conv2/kernel" % i] = (3, 3, f, f)
+        shapes["conv_%d/conv2/bias" % i] = (f,)
+        cin, f = f, f * 2
+    f //= 2
+    net_c = f
+    for i in range(num_layers - 1):
+        f //= 2
+        shapes["up_conv_%d/kernel" % i] = (2, 2, f, net_c)
+        shapes["up_conv_%d/bias" % i] = (f,)
+        cat = f * (3 if dilated_layers else 2)
+        j = num_layers + i
+        shapes["conv_%d/conv1/kernel" % j] = (3, 3, cat, f)
+        shapes["conv_%d/conv1/bias" % j] = (f,)
+        shapes["conv_%d/conv2/kernel" % j] = (3, 3, f, f)
+        shapes["conv_%d/conv2/bias" % j] = (f,)
+        net_c = f
+    shapes["weight_output/kernel"] = (1, 1, net_c, 2)
+    shapes["weight_output/bias"] = (2,)
+    return shapes
+
+
+def glorot_init(num_layers, root_size, dilated_layers, seed=2017):
+    """tf.layers defaults: glorot-uniform kernels, zero biases, drawn in creation order."""
+    rs = np.random.RandomState(seed)
+    out = OrderedDict()
+    for name, shape in variable_shapes(num_layers, root_size, dilated_layers).items():
+        if name.endswith("bias"):
+            out[name] = np.zeros(shape, dtype=np.float32)
+        else:
+            kh, kw, a, b = shape
+            limit = np.sqrt(6.0 / (kh * kw * a + kh * kw * b))
+            out[name] = rs.uniform(-limit, limit, size=shape).astype(np.float32)
+    return out
+
+
+class _Conv:
+    """One 3x3 convolution of the plan: where its operands live and how it is wired."""
+
+    def __init__(self, name, cin, cout, dilation=1):
+        self.name, self.cin, self.cout, self.dilation = name, cin, cout, dilation
+        self.w_fwd = self.w_dgrad = None
+
+
+class UNet:
+    """Static execution plan + state of one U-Net instance on one GPU.
+
+    State: `params` / `grads` / `momentum` are flat fp32 device vectors; `var(name)` returns the
+    TensorFlow-layout view of one variable.  All activations live in preallocated buffers sized
+    for (batch_size, input_size), so a step is a fixed sequence of kernel launches.
+    """
+
+    def __init__(self, num_layers, root_size, dilated_layers, batch_size, input_size,
+                 device="cuda", seed=2017, training=True, params=None):
+        if root_size % 64 != 0:
+            raise ValueError("root_size must be a multiple of 64 (tcgen05 K chunk); got %d" % root_size)
+        if not torch.cuda.is_available():
+            raise RuntimeError("the B200 U-Net engine needs a CUDA device; there is no CPU fallback")
+        self.L, self.root, self.dilated = num_layers, root_size, bool(dilated_layers)
+        self.B, self.S = batch_size, input_size
+        self.device = torch.device(device)
+        self.training = training
+        self.seed = seed
+        self.global_step = 0
+        self._plan_geometry()
+        self._alloc_state(params)
+        self._alloc_buffers()
+        self.pack_weights()
+
+    # ------------------------------------------------------------------ geometry
+    def _plan_geometry(self):
+        L, S = self.L, self.S
+        self.f = [self.root * 2 ** i for i in range(L)]
+        self.in_size = []
+        s = S
+        for i in range(L):
+            self.in_size.append(s)
+            skip = s - 4
+            if skip <= 0:
+                raise AssertionError("input size %d too small for %d layers" % (S, L))
+            if i < L - 1:
+                assert skip % 2 == 0, "level %d size %d not divisible by 2" % (i, skip)
+                s = skip // 2
+        self.skip_size = [s_ - 4 for s_ in self.in_size]
+        net = self.skip_size[L - 1]
+        self.up_size, self.dec_out = [], []
+        for j in range(L - 1):
+            t = 2 * net
+            self.up_size.append(t)
+            net = t - 4
+            self.dec_out.append(net)
+        self.P = net if L > 1 else self.skip_size[0]
+        for j in range(L - 1):
+            i = L - 2 - j
+            assert self.skip_size[i] >= self.up_size[j]
+            if self.dilated:
+                assert self.in_size[i] - 8 >= self.up_size[j]
+
+    def level_of_decoder(self, j):
+        return self.L - 2 - j
+
+    # ------------------------------------------------------------------ state
+    def _alloc_state(self, params):
+        shapes = variable_shapes(self.L, self.root, self.dilated)
+        self.shapes = shapes
+        self.offsets = OrderedDict()
+        off = 0
+        for name, shape in shapes.items():
+            self.offsets[name] = off
+            off += (int(np.prod(shape)) + 63) // 64 * 64  # keep every variable 256-byte aligned
+        self.n_flat = off
+        dev = self.device
+        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
+        self.momentum = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
+        init = params if params is not None else glorot_init(self.L, self.root, self.dilated, self.seed)
+        self.load_state(init)
+
+    def var(self, name, which="params"):
+        flat = getattr(self, which)
+        shape = self.shapes[name]
+        o = self.offsets[name]
+        return flat[o:o + int(np.prod(shape))].view(shape)
+
+    def load_state(self, params, momentum=None):
+        for name in self.shapes:
+            if name in params:
+                self.var(name).copy_(torch.as_tensor(np.asarray(params[name], dtype=np.float32)))
+            if momentum is not None and name in momentum and self.momentum is not None:
+                self.var(name, "momentum").copy_(
+                    torch.as_tensor(np.asarray(momentum[name], dtype=np.float32)))
+
+    def state_dict(self, which="params"):
+        return OrderedDict((n, self.var(n, which).detach().cpu().numpy().copy()) for n in self.shapes)
+
+    def live_variables(self):
+        dead = set()
+        if self.dilated:
+            i = self.L - 1
+            dead = {"conv_dilut_%d/atrous_conv%d/%s" % (i, k, p) for k in (1, 2)
+                    for p in ("kernel", "bias")}
+        return [n for n in self.shapes if n not in dead]
+
+    # ------------------------------------------------------------------ buffers
+    def _bf(self, *shape):
+        return torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+
+    def _alloc_buffers(self):
+        L, B, f = self.L, self.B, self.f
+        tr = self.training
+        self.A1, self.A2, self.Pool = [], [], []
+        self.D1, self.D2 = [], []
+        self.dA1, self.dA2, self.dIn = [], [], []
+        self.dD1, self.dD2 = [], []
+        self.dil_off = []
+        for i in range(L):
+            s = self.in_size[i]
+            self.A1.append(self._bf(B, s - 2, s - 2, f[i]))
+            self.A2.append(self._bf(B, s - 4, s - 4, f[i]))
+            self.Pool.append(self._bf(B, (s - 4) // 2, (s - 4) // 2, f[i]) if i < L - 1 else None)
+            if tr:
+                self.dA1.append(self._bf(B, s - 2, s - 2, f[i]))
+                self.dA2.append(self._bf(B, s - 4, s - 4, f[i]))
+                self.dIn.append(self._bf(B, s, s, f[i - 1]) if i > 0 else None)
+            if self.dilated and i < L - 1:
+                t = self.up_size[L - 2 - i]
+                o2 = (s - 8 - t) // 2
+                self.dil_off.append(o2)
+                self.D1.append(self._bf(B, t + 4, t + 4, f[i]))
+                self.D2.append(self._bf(B, t, t, f[i]))
+                if tr:
+                    self.dD1.append(self._bf(B, t + 4, t + 4, f[i]))
+                    self.dD2.append(self._bf(B, t, t, f[i]))
+            else:
+                self.dil_off.append(None)
+                self.D1.append(None)
+                self.D2.append(None)
+                self.dD1.append(None)
+                self.dD2.append(None)
+        # first layer im2col buffers (Cin = 3 -> 64 padded channels)
+        s0 = self.in_size[0]
+        self.col = self._bf(B, s0 - 2, s0 - 2, 64)
+        self.dcol = self._bf(B, s0 - 2, s0 - 2, 64) if tr else None
+        if self.dilated and L > 1:
+            t0 = self.up_size[L - 2]
+            self.colD = self._bf(B, t0 + 4, t0 + 4, 64)
+            self.dcolD = self._bf(B, t0 + 4, t0 + 4, 64) if tr else None
+        else:
+            self.colD = self.dcolD = None
+        self.U, self.C1, self.C2 = [], [], []
+        self.dCat, self.dC1, self.dC2 = [], [], []
+        for j in range(L - 1):
+            fo = f[L - 2 - j]
+            t = self.up_size[j]
+            self.U.append(self._bf(B, t, t, fo))
+            self.C1.append(self._bf(B, t - 2, t - 2, fo))
+            self.C2.append(self._bf(B, t - 4, t - 4, fo))
+            if tr:
+                self.dCat.append(self._bf(B, t, t, fo * (3 if self.dilated else 2)))
+                self.dC1.append(self._bf(B, t - 2, t - 2, fo))
+                self.dC2.append(self._bf(B, t - 4, t - 4, fo))
+        P = self.P
+        dev = self.device
+        self.probs = torch.empty(B, P, P, dtype=torch.float32, device=dev)
+        self.logits = torch.empty(B, P, P, 2, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        # dropout scratch (dropped copies of pooled tensors / decoder inputs), allocated lazily
+        self._drop_pool = [None] * L
+        self._drop_net = [None] * max(L - 1, 0)
+        # packed bf16 weights
+        self.convs = OrderedDict()
+        for name, shape in self.shapes.items():
+            if not name.endswith("kernel") or name.startswith(("color_space", "weight_output")):
+                continue
+            key = name[:-len("/kernel")]
+            if key.startswith("up_conv"):
+                _, _, cout, cin = shape
+                c = _Conv(key, cin, cout)
+                c.w_fwd = self._bf(4 * cout, cin)
+                c.w_dgrad = self._bf(cin, 4 * cout) if tr else None
+            else:
+                _, _, cin, cout = shape
+                c = _Conv(key, cin, cout, 2 if "atrous" in key else 1)
+                if cin == 3:
+                    c.w_fwd = torch.zeros(cout, 64, dtype=torch.bfloat16, device=dev)
+                    c.w_dgrad = torch.zeros(64, cout, dtype=torch.bfloat16, device=dev) if tr else None
+                    c.dw_stage = torch.zeros(64, cout, dtype=torch.float32, device=dev) if tr else None
+                else:
+                    c.w_fwd = self._bf(cout, 9 * cin)
+                    c.w_dgrad = self._bf(cin, 9 * cout) if tr else None
+            self.convs[key] = c
+        if self.dilated:  # dead pair: weights exist, never packed or evaluated
+            for k in (1, 2):
+                self.convs.pop("conv_dilut_%d/atrous_conv%d" % (L - 1, k), None)
+
+    # ------------------------------------------------------------------ weights
+    def pack_weights(self):
+        """fp32 master (TensorFlow layouts) -> bf16 GEMM operand layouts; run after every update."""
+        for key, c in self.convs.items():
+            w = self.var(key + "/kernel")
+            if key.startswith("up_conv"):
+                ops.cast_bf16(w, c.w_fwd)
+                if c.w_dgrad is not None:
+                    ops.pack_conv_fwd(w, c.w_dgrad, 1, 4 * c.cout, c.cin)
+            elif c.cin == 3:
+                ops.pack_conv_fwd(w, c.w_fwd, 1, 27, c.cout, ld=64)
+                if c.w_dgrad is not None:
+                    ops.pack_conv_dgrad(w, c.w_dgrad, 1, 27, c.cout)
+            else:
+                ops.pack_conv_fwd(w, c.w_fwd, 9, c.cin, c.cout)
+                if c.w_dgrad is not None:
+                    ops.pack_conv_dgrad(w, c.w_dgrad, 9, c.cin, c.cout)
+
+    # ------------------------------------------------------------------ forward
+    def _site_seed(self, site):
+        return (self.seed * 1000003 + self.global_step * 131 + site) & 0xFFFFFFFFFFFF
+
+    def forward(self, images, labels=None, keep=1.0, want_logits=False):
+        """images: fp32 [B,S,S,3] device tensor in [0,1].  Fills self.probs (and self.loss and the
+        head gradients when labels (uint8 [B,P,P]) are given).  Returns probs."""
+        L, f = self.L, self.f
+        assert images.shape == (self.B, self.S, self.S, 3) and images.dtype == torch.float32
+        self._images = images
+        self._keep = float(keep)
+        w1 = self.var("color_space_adjust/kernel")
+        b1 = self.var("color_space_adjust/bias")
+        bias = lambda key: self.var(key + "/bias")
+        drop = keep < 1.0
+        site = 0
+        net = None
+        for i in range(L):
+            reg1, reg2 = self.convs["conv_%d/conv1" % i], self.convs["conv_%d/conv2" % i]
+            dil_live = self.dilated and i < L - 1
+            o2 = self.dil_off[i]
+            if i == 0:
+                seed0 = self._site_seed(site)
+                ops.color_im2col(images, w1, b1, 1, 0, 0, self.col, keep, seed0)
+                ops.conv_gemm([(self.col, 0, 0)], [(0, 0)], reg1.w_fwd, self.A1[0], f[0],
+                              bias=bias(reg1.name), relu=True)
+                if dil_live:
+                    d1 = self.convs["conv_dilut_0/atrous_conv1"]
+                    ops.color_im2col(images, w1, b1, 2, o2, o2, self.colD, keep, seed0)
+                    ops.conv_gemm([(self.colD, 0, 0)], [(0, 0)], d1.w_fwd, self.D1[0], f[0],
+                                  bias=bias(d1.name), relu=True)
+            else:
+                src = self.Pool[i - 1]
+                if drop:
+                    if self._drop_pool[i] is None:
+                        self._drop_pool[i] = torch.empty_like(src)
+                    ops.dropout(src, self._drop_pool[i], keep, self._site_seed(site))
+                    src = self._drop_pool[i]
+                net = src
+                ops.conv3x3_fwd([(src, 0, 0)], reg1.w_fwd, bias(reg1.name), self.A1[i])
+                if dil_live:
+                    d1 = self.convs["conv_dilut_%d/atrous_conv1" % i]
+                    ops.conv3x3_fwd([(src, o2, o2)], d1.w_fwd, bias(d1.name), self.D1[i], dilation=2)
+            site += 1
+            if dil_live:
+                d2 = self.convs["conv_dilut_%d/atrous_conv2" % i]
+                ops.conv3x3_fwd([(self.D1[i], 0, 0)], d2.w_fwd, bias(d2.name), self.D2[i], dilation=2)
+            ops.conv3x3_fwd([(self.A1[i], 0, 0)], reg2.w_fwd, bias(reg2.name), self.A2[i])
+            if i < L - 1:
+                ops.maxpool2x2(self.A2[i], self.Pool[i])
+        net = self.A2[L - 1]
+        self._dec_in = []
+        for j in range(L - 1):
+            i = L - 2 - j
+            up = self.convs["up_conv_%d" % j]
+            c1, c2 = self.convs["conv_%d/conv1" % (L + j)], self.convs["conv_%d/conv2" % (L + j)]
+            if drop:
+                if self._drop_net[j] is None:
+                    self._drop_net[j] = torch.empty_like(net)
+                ops.dropout(net, self._drop_net[j], keep, self._site_seed(site))
+                net = self._drop_net[j]
+            site += 1
+            self._dec_in.append(net)
+            ops.upconv2x2_fwd(net, up.w_fwd, bias(up.name), self.U[j])
+            t = self.up_size[j]
+            so = (self.skip_size[i] - t) // 2
+            srcs = [(self.A2[i], so, so)]
+            if self.dilated:
+                srcs.append((self.D2[i], 0, 0))
+            srcs.append((self.U[j], 0, 0))
+            ops.conv3x3_fwd(srcs, c1.w_fwd, bias(c1.name), self.C1[j])
+            ops.conv3x3_fwd([(self.C1[j], 0, 0)], c2.w_fwd, bias(c2.name), self.C2[j])
+            net = self.C2[j]
+        self._last = net
+        wh = self.var("weight_output/kernel").view(-1, 2)
+        bh = self.var("weight_output/bias")
+        if labels is None:
+            ops.head(net, wh, bh, probs=self.probs, logits=self.logits if want_logits else None)
+        else:
+            assert self.training
+            self.loss.zero_()
+            dlast = self.dC2[L - 2] if L > 1 else self.dA2[0]
+            ops.head(net, wh, bh, labels=labels, probs=self.probs,
+                     logits=self.logits if want_logits else None, loss=self.loss, dz=dlast,
+                     dw=self.var("weight_output/kernel", "grads").view(-1, 2),
+                     db=self.var("weight_output/bias", "grads"))
+        return self.probs
+
+    # ------------------------------------------------------------------ backward
+    def _conv_bwd(self, conv, srcs, dz, dx, mask=None, accumulate=False, need_dx=True):
+        """wgrad + bias grad (+ dgrad) of one 3x3 convolution."""
+        g = lambda n: self.var(conv.name + "/" + n, "grads")
+        ops.conv3x3_wgrad(srcs, dz, g("kernel").view(-1, conv.cout), dilation=conv.dilation)
+        ops.bias_grad(dz, g("bias"))
+        if need_dx:
+            ops.conv3x3_dgrad(dz, conv.w_dgrad, dx, dilation=conv.dilation, mask=mask,
+                              accumulate=accumulate)
+
+    def _first_bwd(self, conv, col, dcol, dz, dilation, oy, ox):
+        """Cin = 3 convolution through its im2col matrix, plus d(color_space_adjust)."""
+        g = lambda n: self.var(conv.name + "/" + n, "grads")
+        conv.dw_stage.zero_()
+        ops.wgrad_gemm([(col, 0, 0)], [(0, 0)], dz, (0, 0), conv.dw_stage, (dz.shape[1], dz.shape[2]))
+        g("kernel").view(27, conv.cout).add_(conv.dw_stage[:27])
+        ops.bias_grad(dz, g("bias"))
+        ops.conv_gemm([(dz, 0, 0)], [(0, 0)], conv.w_dgrad, dcol, 64)
+        ops.color_im2col_bwd(self._images, dcol, dilation, oy, ox,
+                             self.var("color_space_adjust/kernel", "grads"),
+                             self.var("color_space_adjust/bias", "grads"), self._keep,
+                             self._site_seed(0))
+
+    def backward(self):
+        """Gradients of the mean cross-entropy w.r.t. every live variable (into self.grads, which
+        the caller zeroed before forward(labels=...))."""
+        L, f = self.L, self.f
+        keep = self._keep
+        drop = keep < 1.0
+        n_sites = 2 * L - 1
+        for j in range(L - 2, -1, -1):
+            i = L - 2 - j
+            fo = f[i]
+            up = self.convs["up_conv_%d" % j]
+            c1, c2 = self.convs["conv_%d/conv1" % (L + j)], self.convs["conv_%d/conv2" % (L + j)]
+            t = self.up_size[j]
+            so = (self.skip_size[i] - t) // 2
+            self._conv_bwd(c2, [(self.C1[j], 0, 0)], self.dC2[j], self.dC1[j], mask=self.C1[j])
+            srcs = [(self.A2[i], so, so)]
+            if self.dilated:
+                srcs.append((self.D2[i], 0, 0))
+            srcs.append((self.U[j], 0, 0))
+            self._conv_bwd(c1, srcs, self.dC1[j], self.dCat[j])
+            dcat = self.dCat[j]
+            if self.dilated:
+                ops.relu_mask(self.D2[i], dcat[..., fo:2 * fo], self.dD2[i])
+            d_up = dcat[..., (2 if self.dilated else 1) * fo:]
+            x_in = self._dec_in[j]
+            g = lambda n: self.var(up.name + "/" + n, "grads")
+            ops.upconv2x2_wgrad(d_up, x_in, g("kernel").view(4 * up.cout, up.cin))
+            ops.bias_grad(d_up, g("bias"))
+            # gradient into the tensor that fed the transpose conv (previous decoder output, or
+            # the bottom of the encoder), with its ReLU mask fused
+            if j > 0:
+                dst, act = self.dC2[j - 1], self.C2[j - 1]
+            else:
+                dst, act = self.dA2[L - 1], self.A2[L - 1]
+            ops.upconv2x2_dgrad(d_up, up.w_dgrad, dst, mask=x_in if drop else act)
+            if drop:
+                ops.dropout(dst, dst, keep, self._site_seed(L + j))
+        for i in range(L - 1, -1, -1):
+            reg1, reg2 = self.convs["conv_%d/conv1" % i], self.convs["conv_%d/conv2" % i]
+            dil_live = self.dilated and i < L - 1
+            if i < L - 1:
+                j = L - 2 - i
+                t = self.up_size[j]
+                so = (self.skip_size[i] - t) // 2
+                d_in_next = self.dIn[i + 1]
+                if drop:
+                    ops.dropout(d_in_next, d_in_next, keep, self._site_seed(i + 1))
+                ops.skip_grad(self.A2[i], d_in_next, self.dCat[j][..., :f[i]], (so, so), self.dA2[i])
+            self._conv_bwd(reg2, [(self.A1[i], 0, 0)], self.dA2[i], self.dA1[i], mask=self.A1[i])
+            if i > 0:
+                src = self._drop_pool[i] if drop else self.Pool[i - 1]
+                self._conv_bwd(reg1, [(src, 0, 0)], self.dA1[i], self.dIn[i])
+            else:
+                self._first_bwd(reg1, self.col, self.dcol, self.dA1[0], 1, 0, 0)
+            if dil_live:
+                d1 = self.convs["conv_dilut_%d/atrous_conv1" % i]
+                d2 = self.convs["conv_dilut_%d/atrous_conv2" % i]
+                o2 = self.dil_off[i]
+                self._conv_bwd(d2, [(self.D1[i], 0, 0)], self.dD2[i], self.dD1[i], mask=self.D1[i])
+                if i > 0:
+                    src = self._drop_pool[i] if drop else self.Pool[i - 1]
+                    tt = self.D1[i].shape[1] + 4
+                    win = self.dIn[i][:, o2:o2 + tt, o2:o2 + tt, :]
+                    self._conv_bwd(d1, [(src, o2, o2)], self.dD1[i], win, accumulate=True)
+                else:
+                    self._first_bwd(d1, self.colD, self.dcolD, self.dD1[0], 2, o2, o2)
+
+    # ------------------------------------------------------------------ optimizer
+    def learning_rate(self, lr0):
+        """tf.train.exponential_decay(lr, global_step, 1000, 0.95, staircase=True)."""
+        return lr0 * 0.95 ** (self.global_step // 1000)
+
+    def apply_gradients(self, lr0, momentum, grad_scale=1.0):
+        ops.momentum_sgd(self.params, self.momentum, self.grads, self.learning_rate(lr0), momentum,
+                         grad_scale)
+        self.global_step += 1
+        self.pack_weights()
+
+    def train_step(self, images, labels, lr0=0.01, momentum=0.9, keep=1.0, allreduce=None):
+        """forward + backward + momentum update; returns the device scalar loss tensor."""
+        self.grads.zero_()
+        self.forward(images, labels, keep)
+        self.backward()
+        scale = 1.0
+        if allreduce is not None:
+            scale = allreduce(self.grads)
+        self.apply_gradients(lr0, momentum, scale)
+        return self.loss
+
+
+class Placeholder:
+    """Stand-in for tf.placeholder: only carries the static shape [B, S, S, 3]."""
+
+    def __init__(self, shape, name="patches"):
+        self.shape, self.name = tuple(shape), name
+
+
+def forward(X, num_layers, root_size, dilated_layers, dropout_keep=None, params=None, seed=2017):
+    """Build the U-Net (src/unet.py:12-97).
+
+    X is either a `Placeholder` (static shape, like the reference's graph mode) -- the planned
+    `UNet` engine is returned -- or an array [B,S,S,3] in [0,1], in which case the network is run
+    once (with `params`, a dict keyed by TensorFlow variable names, or a fresh glorot init) and the
+    logits [B,P,P,2] are returned as a NumPy array.
+    """
+    if isinstance(X, Placeholder):
+        b, s = X.shape[0], X.shape[1]
+        return UNet(num_layers, root_size, dilated_layers, b, s, seed=seed, params=params)
+    x = torch.as_tensor(np.asarray(X, dtype=np.float32)).cuda()
+    net = UNet(num_layers, root_size, dilated_layers, x.shape[0], x.shape[1], seed=seed,
+               training=False, params=params)
+    keep = 1.0 if dropout_keep is None else float(dropout_keep)
+    net.forward(x, keep=keep, want_logits=True)
+    return net.logits.cpu().numpy()

@@ -1,0 +1,152 @@
+"""Pins the CPU oracle: images_oracle against golden vectors made by the reference's own
+src/images.py (tests/golden/make_golden.py), unet_oracle against an independent NumPy loop nest
+and against the properties the reference documents."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import images_oracle as IO
+from oracle import unet_oracle as UO
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "images_golden.npz"))
+
+
+def test_mirror_border_golden():
+    assert np.array_equal(IO.mirror_border(G["mirror_in4"], 4), G["mirror_out4_n4"])
+    assert np.array_equal(IO.mirror_border(G["mirror_in3"], 7), G["mirror_out3_n7"])
+    # [1,0 | 0,1,2,3,4 | 4,3]
+    row = np.arange(5, dtype=np.float32).reshape(1, 1, 5)
+    assert IO.mirror_border(np.repeat(row, 5, axis=1), 2)[0, 2].tolist() == [1, 0, 0, 1, 2, 3, 4, 4, 3]
+
+
+def test_extract_patches_golden():
+    x = G["extract_in"]
+    assert np.array_equal(IO.extract_patches(x, 8, stride=4), G["extract_p8_s4"])
+    assert np.array_equal(IO.extract_patches(x, 10), G["extract_p10_nostride"])
+    assert np.array_equal(IO.extract_patches(x[..., 0], 12, stride=8), G["extract3d_p12_s8"])
+    assert IO.extract_patches(x, 8, stride=4).dtype == np.float64
+    with pytest.raises(AssertionError):
+        IO.extract_patches(x, 8, stride=5)
+
+
+def test_reference_shape_tests():
+    """The shape assertions of the reference's own src/test_images.py:11-121."""
+    imgs = np.zeros((2, 608, 608, 3), dtype=np.float32)
+    assert IO.extract_patches(imgs, 128, 16).shape == (2 * 31 * 31, 128, 128, 3)
+    assert IO.extract_patches(imgs[:1], 32).shape == (361, 32, 32, 3)
+    p = IO.extract_patches(np.zeros((1, 400, 400, 3), dtype=np.float32), 80)
+    assert p.shape == (25, 80, 80, 3)
+    assert IO.images_from_patches(p.reshape(1, 25, 80, 80, 3)).shape == (1, 400, 400, 3)
+
+
+def test_images_from_patches_golden():
+    assert np.array_equal(IO.images_from_patches(G["from_patches_in"], stride=4), G["from_patches_s4"])
+    assert np.array_equal(IO.images_from_patches(G["from_patches_in"]), G["from_patches_nostride"])
+    assert np.array_equal(IO.images_from_patches(G["from_patches_in64"], stride=3), G["from_patches64_s3"])
+    x = np.random.RandomState(0).rand(2, 20, 20, 3)
+    pt = IO.extract_patches(x, 8, stride=4).reshape(2, 16, 8, 8, 3)
+    assert np.abs(IO.images_from_patches(pt, stride=4) - x).max() == 0.0  # exact round trip
+
+
+def test_ensemble_golden():
+    assert np.array_equal(IO.image_augmentation_ensemble(G["ens_in"]), G["ens_out"])
+    assert np.array_equal(IO.invert_image_augmentation_ensemble(G["inv_in"]), G["inv_out"])
+    m = np.random.RandomState(1).rand(3, 9, 9, 1)
+    rt = IO.invert_image_augmentation_ensemble(IO.image_augmentation_ensemble(m))
+    assert np.abs(rt - m).max() < 1e-15
+    # flip_ud x rot90^k enumerates the 8 elements of D4, variants of the ensemble are 6 of them
+    x = np.arange(16.0).reshape(4, 4)
+    assert len({IO.d4(x, op).tobytes() for op in range(8)}) == 8
+    ens_ops = [0, 4 | 2, 4, 1, 2, 3]
+    e = IO.image_augmentation_ensemble(x.reshape(1, 4, 4, 1))
+    for v, op in enumerate(ens_ops):
+        assert np.array_equal(e[v, :, :, 0], IO.d4(x, op))
+
+
+def test_crop_golden():
+    assert np.array_equal(IO.crop_imgs(G["crop_in"], 8), G["crop_out8"])
+
+
+@pytest.mark.parametrize("angle", [15, 30, 45, 60, 75, 90])
+def test_rotate_golden(angle):
+    got = IO.rotate_nn(G["rot_in"], angle)
+    ref = G["rot_%d" % angle]
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+
+
+def test_expand_and_rotate_golden():
+    assert np.array_equal(IO.expand_and_rotate(G["expand_in"], [0, 15, 45, 75], 6), G["expand_off6"])
+    assert np.array_equal(IO.expand_and_rotate(G["expand_in"][..., 0], [30, 60], 0), G["expand3d_off0"])
+
+
+def test_quantize_golden():
+    assert np.array_equal(IO.quantize_mask(G["quant_in"], 0.25, 16), G["quant_out"])
+    assert IO.patch_f1(G["quant_in"], G["quant_in"]) == 1.0
+
+
+# ------------------------------------------------------------------ U-Net oracle
+def test_input_size_needed():
+    """unet.py:100-115; closed form S = P + 12 * 2^(L-1) - 8 (report/report.tex:50)."""
+    assert UO.input_size_needed(388, 4) == 476
+    assert UO.input_size_needed(388, 5) == 572
+    assert UO.input_size_needed(388, 6) == 764
+    for L in (2, 3, 4, 5, 6):
+        assert UO.input_size_needed(2 ** L * 3 + 4, L) == 2 ** L * 3 + 4 + 12 * 2 ** (L - 1) - 8
+    with pytest.raises(AssertionError):
+        UO.input_size_needed(390, 4)
+
+
+def test_variable_inventory():
+    """Parameter counts of SURVEY.md appendix B / report.tex:50."""
+    n = lambda L, r, d: sum(int(np.prod(s)) for s in UO.variable_shapes(L, r, d).values())
+    assert n(6, 64, True) == 212403278
+    assert n(4, 64, False) == 7697422
+    assert n(5, 64, False) == 31031822
+    dead = UO.dead_variables(6, True)
+    shapes = UO.variable_shapes(6, 64, True)
+    assert n(6, 64, True) - sum(int(np.prod(shapes[k])) for k in dead) == 155776078
+
+
+def test_conv_against_loop_nest():
+    rs = np.random.RandomState(3)
+    x = rs.randn(2, 9, 9, 5).astype(np.float32)
+    w = rs.randn(3, 3, 5, 4).astype(np.float32)
+    b = rs.randn(4).astype(np.float32)
+    for d in (1, 2):
+        got = UO.conv2d_valid(torch.tensor(x), torch.tensor(w), torch.tensor(b), d).numpy()
+        assert np.allclose(got, UO.conv2d_valid_loops(x, w, b, d), atol=1e-4)
+    wt = rs.randn(2, 2, 6, 5).astype(np.float32)
+    bt = rs.randn(6).astype(np.float32)
+    got = UO.conv2d_transpose_2x2(torch.tensor(x), torch.tensor(wt), torch.tensor(bt)).numpy()
+    assert np.allclose(got, UO.conv2d_transpose_2x2_loops(x, wt, bt), atol=1e-4)
+
+
+@pytest.mark.parametrize("dilated", [False, True])
+def test_forward_shapes_and_step(dilated):
+    L, root, P = 3, 8, 20
+    S = UO.input_size_needed(P, L)
+    params = UO.init_params(L, root, dilated, seed=2017)
+    rs = np.random.RandomState(0)
+    X = rs.rand(2, S, S, 3).astype(np.float32)
+    labels = (rs.rand(2, P, P) < 0.3).astype(np.int64)
+    accs = {k: np.zeros_like(v) for k, v in params.items()}
+    loss, probs, grads, new_p, new_a, acts = UO.train_step(
+        X, labels, params, accs, L, root, dilated, lr=0.01, momentum=0.9, want_acts=True)
+    assert acts["logits"].shape == (2, P, P, 2)
+    assert probs.shape == (2, P, P) and 0 < loss < 5
+    for k in UO.dead_variables(L, dilated):
+        assert grads[k] is None and np.array_equal(new_p[k], params[k])
+    k = "conv_0/conv1/kernel"
+    assert np.allclose(new_a[k], grads[k]) and np.allclose(new_p[k], params[k] - 0.01 * grads[k])
+    # fp64 run agrees with fp32 run (oracle self-consistency)
+    loss64 = UO.train_step(X, labels, params, accs, L, root, dilated, 0.01, 0.9, dtype=torch.float64)[0]
+    assert abs(loss64 - loss) < 1e-5
+
+
+def test_learning_rate_staircase():
+    assert UO.learning_rate(0.01, 999) == 0.01
+    assert abs(UO.learning_rate(0.01, 1000) - 0.0095) < 1e-12
+    assert abs(UO.learning_rate(0.01, 2500) - 0.01 * 0.95 ** 2) < 1e-12

@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 U-Net hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): training of the 6-layer dilated U-Net (root 64), batch 32
+of 388^2 output patches (764^2 inputs) per GPU, bf16 tensor-core math with fp32 accumulate and
+fp32 master weights, momentum SGD.  One step = forward + backward + (all-reduce) + update.
+`value` is whole-job patches/s with the batch resident in HBM, `e2e` the same metric through the
+public API (ConvolutionalModel.train_batch) with pinned host buffers copied in every step and
+the loss + probabilities read back.  Data are synthetic (seed 2017), weights random glorot init.
+Inputs per step (19 GB of activations) are far larger than the 126 MB L2, so no explicit flush.
+
+`--impl reference` times the CPU oracle restatement of the reference's TensorFlow path
+(oracle/unet_oracle.py; TF 1.4 itself cannot be installed here) on the host cores, one patch per
+step of the same model.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "U-Net train patches/s (388^2)"
+UNIT = "patches/s"
+CFG = dict(num_layers=6, root_size=64, dilated_layers=True, patch_size=388, batch_size=32)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), \
+            d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+                power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples drawing more than half of the maximum observed power
+        pmax = max(power)
+        load = [s for s, w in zip(sm, power) if w >= 0.5 * pmax] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(smax)),
+                "power_w_max": pmax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_batch(B, S, P, seed):
+    rs = np.random.RandomState(seed)
+    x = rs.rand(B, S, S, 3).astype(np.float32)
+    lab = (rs.rand(B, P, P) < 0.25)
+    # smooth-ish road-like field: 9x9 box filter then threshold
+    k = 9
+    f = lab.astype(np.float32)
+    c = np.cumsum(np.cumsum(np.pad(f, ((0, 0), (k // 2 + 1, k // 2), (k // 2 + 1, k // 2))), 1), 2)
+    box = c[:, k:, k:] - c[:, :-k, k:] - c[:, k:, :-k] + c[:, :-k, :-k]
+    return x, (box / (k * k) >= 0.25).astype(np.uint8)
+
+
+# ------------------------------------------------------------------ CPU oracle timing
+def time_oracle(steps, warmup, threads=None):
+    """The oracle (port of the reference's TF graph) on the host: fwd + bwd + momentum update of
+    the SAME model, one 764^2 -> 388^2 patch per step, fp32."""
+    import torch
+    from oracle import unet_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    L, root, dil, P = CFG["num_layers"], CFG["root_size"], CFG["dilated_layers"], CFG["patch_size"]
+    S = O.input_size_needed(P, L)
+    params = O.init_params(L, root, dil, seed=2017)
+    tp = O.to_torch(params, requires_grad=True)
+    accs = {k: torch.zeros_like(v) for k, v in tp.items()}
+    x, lab = synthetic_batch(1, S, P, 2017)
+    xt, lt = torch.tensor(x), torch.tensor(lab.astype(np.int64))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for v in tp.values():
+            v.grad = None
+        logits = O.forward(xt, tp, L, root, dil)
+        loss, _ = O.loss_and_probs(logits, lt)
+        loss.backward()
+        with torch.no_grad():
+            for k, v in tp.items():
+                if v.grad is None:
+                    continue
+                accs[k].mul_(0.9).add_(v.grad)
+                v.sub_(0.01 * accs[k])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return 1.0 / float(np.mean(times)), float(np.mean(times)), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warmup = max(1, min(args.warmup, 2))
+    v, sec, threads = time_oracle(steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "U-Net L=6 root=64 dilated, 764^2->388^2 patches, fwd+bwd+momentum SGD "
+                               "(BASELINE.json configs[1]); CPU arm runs batch 1 per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d steps of batch 1 of the same model, fp32 torch-CPU oracle" % steps},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from road_segmentation_unet_b200 import ops, unet
+    from road_segmentation_unet_b200 import tf_aerial_images as tfa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group(backend="nccl")
+
+    B = args.batch or CFG["batch_size"]
+    opts = tfa.Options()
+    opts.batch_size, opts.num_layers, opts.root_size = B, CFG["num_layers"], CFG["root_size"]
+    opts.dilated_layers, opts.patch_size = CFG["dilated_layers"], CFG["patch_size"]
+    opts.dropout, opts.lr, opts.momentum, opts.image_augmentation = 1.0, 0.01, 0.9, False
+    opts.num_gpu = world
+    model = tfa.ConvolutionalModel(opts, None)
+    net = model.net
+    S, P = model.input_size, opts.patch_size
+    xh, lh = synthetic_batch(B, S, P, 2017 + rank)
+    x = torch.tensor(xh).cuda()
+    lab = torch.tensor(lh).cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        net.grads.zero_()
+        net.forward(x, lab, keep=1.0)
+        net.backward()
+        scale = model._reducer.finish() if model._reducer is not None else 1.0
+        net.apply_gradients(opts.lr, opts.momentum, scale)
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(W):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lib = ops._lib.load()
+    lib.rsu_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        device_step()
+    e1.record()
+    barrier()
+    launches = int(lib.rsu_launch_count())
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(net.loss.item())
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / K
+    value = world * B * K / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host batch in, loss + probabilities out
+    xp = torch.from_numpy(xh).pin_memory()
+    lp = torch.from_numpy(lh).pin_memory()
+    for _ in range(2):
+        model.train_batch(xp, lp)
+    barrier()
+    t0 = time.perf_counter()
+    ke = max(2, min(K, 10))
+    for _ in range(ke):
+        model.train_batch(xp, lp)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * ke / e2e_s
+    h2d = B * S * S * 3 * 4 + B * P * P
+    d2h = B * P * P * 4 + 4
+
+    # ---- roofline of the dominant kernel: CUDA events around every tcgen05 launch (same steps,
+    # instrumented pass so that the headline region above stays free of event records)
+    roof = None
+    extra = {}
+    if rank == 0:
+        peak, peak_sus, hbm, src = measured_peaks()
+        ops.profile_start()
+        kp = min(K, 3)
+        for _ in range(kp):
+            device_step()
+        rec = ops.profile_stop()
+        by_kind = {}
+        for kind, layer, fl, t_ms in rec:
+            a = by_kind.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += fl
+            a[1] += t_ms
+            a[2] += 1
+        conv = by_kind.get("conv_gemm", [0.0, 1e-9, 1])
+        wg = by_kind.get("wgrad_gemm", [0.0, 1e-9, 1])
+        conv_tf = conv[0] / (conv[1] * 1e-3) / 1e12
+        wg_tf = wg[0] / (wg[1] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": conv_tf, "peak": peak_sus, "unit": "TFLOP/s",
+                "frac": conv_tf / peak_sus, "traffic": None,
+                "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: forward + data gradients)",
+                "launches_per_step": conv[2] // kp, "ms_per_step": conv[1] / kp,
+                "alg_flops_per_step": conv[0] / kp,
+                "peak_source": "%s sustained cuBLAS bf16 (MEASURED_PEAKS.json), kernel timed inside a long step" % src}
+        f_alg = 3 * sum(unet.plan_flops(CFG["num_layers"], CFG["root_size"], CFG["dilated_layers"],
+                                        CFG["patch_size"]).values())
+        net_tf = value / world * f_alg / 1e12
+        extra = {
+            "roofline_wgrad": {"bound": "tensor", "achieved": wg_tf, "peak": peak_sus, "unit": "TFLOP/s",
+                               "frac": wg_tf / peak_sus, "launches_per_step": wg[2] // kp,
+                               "ms_per_step": wg[1] / kp, "kernel": "wgrad_gemm_kernel"},
+            "roofline_network": {"bound": "tensor", "achieved": net_tf, "peak": peak, "unit": "TFLOP/s",
+                                 "frac": net_tf / peak, "frac_of_sustained": net_tf / peak_sus,
+                                 "alg_flops_per_patch": f_alg,
+                                 "note": "per-GPU patches/s x 3 x F_min / measured burst bf16 peak"},
+            "other_kernels_ms_per_step": ms_per_step - (conv[1] + wg[1]) / kp,
+        }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, sec, threads = time_oracle(2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "2 timed steps (after 1 warm-up) of batch 1 of the same L=6 dilated 764^2->388^2 "
+                         "model, fwd+bwd+momentum update, fp32 torch-CPU oracle (%.1f s/step)" % sec}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "U-Net num_layers=6 root_size=64 --dilated_layers, batch %d/GPU of "
+                                   "764^2->388^2 patches, momentum SGD lr 0.01 mu 0.9, dropout 1.0 "
+                                   "(BASELINE.json configs[1])" % B,
+                       "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2": "inputs larger than L2 (>= 19 GB of activations per step)",
+                       "timing": "CUDA events on the launch stream, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": ke, "api": "tf_aerial_images.ConvolutionalModel.train_batch (pinned host batch in, "
+                                        "loss + probabilities read back every step)"},
+            "gpu_launches": launches, "loss": loss_val, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 32 = the named config)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,20 +159,26 @@ int rsu_momentum_sgd(float* w, float* acc, const float* g, long long n, float lr
 int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* out, void* stream);
 /* One element of the dihedral group per image: op = flip_ud (bit 2) then rot90^k (bits 0-1),
  * counter-clockwise like np.rot90 / tf.image.rot90 (images.py:376-417,
- * tf_aerial_images.py:173-210).  esize = bytes per pixel element group (C*sizeof). */
+ * tf_aerial_images.py:173-210).  pixel_bytes = bytes per pixel (C * sizeof element); any value. */
 int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
                      const unsigned char* ops /* device [N] */, void* stream);
-/* images.extract_patches (images.py:35-85): x-outer / y-inner patch order; fp32. */
+/* images.extract_patches (images.py:35-85): x-outer / y-inner patch order; fp32.  Only patches
+ * [k_begin, k_begin + k_count) of the N*side*side patch list are written (k_count < 0 = all that
+ * follow k_begin), so a prediction batch never materialises the whole patch tensor. */
 int rsu_extract_patches(const float* in, int N, int H, int W, int C, int patch, int stride,
-                        float* out, void* stream);
-/* images.images_from_patches (images.py:131-164): overlap average in gather form. */
+                        long long k_begin, long long k_count, float* out, void* stream);
+/* images.images_from_patches (images.py:131-164): overlap average in gather form (fp64 sums in
+ * the reference's order, no atomics).  `patches` points at patch k_begin of the list; with
+ * normalize = 0 the un-divided partial sum of that slice is written (sharded prediction). */
 int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int stride,
-                        float* out, void* stream);
-/* crop_imgs(rotate_imgs(x, angle), crop) (images.py:313-373): nearest-neighbour rotation with
- * scipy.ndimage.rotate(order=0, reshape=True, cval=0) semantics followed by the centre crop.
- * cos_a / sin_a are the host-computed cosine / sine of the angle (scipy uses cosdg / sindg). */
-int rsu_rotate_nn_crop(const float* in, int N, int H, int C, double cos_a, double sin_a, int crop,
-                       float* out, void* stream);
+                        long long k_begin, long long k_count, int normalize, float* out,
+                        void* stream);
+/* crop_imgs(rotate_imgs(x, angle), crop) (images.py:313-373): nearest-neighbour affine resampling
+ * with scipy.ndimage.rotate(order=0, mode='constant', cval=0) semantics.  The caller passes
+ * SciPy's geometry -- the 2x2 matrix [[c, s], [-s, c]] and the offset in_center - R*out_center
+ * (host arrays) -- and the window [crop0, crop0+crop)^2 of the rotated image to produce. */
+int rsu_rotate_nn_crop(const float* in, int N, int H, int C, const double* matrix_host,
+                       const double* offset_host, int crop0, int crop, float* out, void* stream);
 /* invert_image_augmentation_ensemble (images.py:399-417): average of the 6 un-transformed masks. */
 int rsu_ensemble_invert(const float* masks /* [6N,S,S] */, int N, int S, float* out, void* stream);
 

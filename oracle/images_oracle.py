@@ -98,8 +98,9 @@ def rotate_nn(imgs, angle):
     rot, offset, out_shape = rotate_params(side, c, s)
     oy, ox = np.meshgrid(np.arange(out_shape[0], dtype=np.float64),
                          np.arange(out_shape[1], dtype=np.float64), indexing="ij")
-    iy = rot[0, 0] * oy + rot[0, 1] * ox + offset[0]
-    ix = rot[1, 0] * oy + rot[1, 1] * ox + offset[1]
+    # SciPy's NI_GeometricTransform accumulates shift first, then one product per axis
+    iy = (offset[0] + oy * rot[0, 0]) + ox * rot[0, 1]
+    ix = (offset[1] + oy * rot[1, 0]) + ox * rot[1, 1]
     ry = np.floor(iy + 0.5).astype(np.int64)
     rx = np.floor(ix + 0.5).astype(np.int64)
     ok = (iy >= 0) & (iy <= side - 1) & (ix >= 0) & (ix <= side - 1)

@@ -154,15 +154,50 @@ def conv2d_transpose_2x2_loops(x, w, b):
     return y + b.astype(np.float64)
 
 
+class _RoundBF16(torch.autograd.Function):
+    """Round-to-nearest-even to bfloat16 in the forward AND in the backward direction."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().to(g.dtype)
+
+
+def _with_bf16_storage(conv_fn):
+    """Storage-precision model of the device path: operands and results of every tensor-core
+    convolution are bf16 in memory (fp32 accumulate), forward and backward.  The 1x1
+    color_space_adjust and weight_output layers are evaluated in fp32 on the device too."""
+    def wrapped(x, w, b, *a):
+        if w.shape[0] == 1 and w.shape[1] == 1:
+            return conv_fn(x, w, b, *a)
+        r = _RoundBF16.apply
+        return r(conv_fn(r(x), r(w), b, *a))
+    return wrapped
+
+
 # ----------------------------------------------------------------------------- forward
 def forward(X, params, num_layers, root_size, dilated_layers, dropout_scales=None, keep=None,
-            acts=None):
+            acts=None, storage=None):
     """src/unet.py:12-97.  X: torch [B,S,S,3]; params: name -> torch tensor.
 
     dropout_scales: optional list of per-site multiplicative masks (0 or 1/keep), in the order
     the reference calls tf.nn.dropout (one per encoder block, one per decoder block); TF's own
     random stream is not reproducible so masks are inputs.  acts (dict) collects activations.
+    storage: None = the reference's fp32 everywhere; "bf16" = same algorithm with activations,
+    weights and gradients of the 3x3 / transpose convolutions rounded to bf16 where the device
+    path stores bf16 (used to separate kernel errors from the precision floor).
     """
+    conv2d_valid = globals()["conv2d_valid"]
+    conv2d_transpose_2x2 = globals()["conv2d_transpose_2x2"]
+    if storage == "bf16":
+        conv2d_valid = _with_bf16_storage(conv2d_valid)
+        conv2d_transpose_2x2 = _with_bf16_storage(conv2d_transpose_2x2)
+    else:
+        assert storage is None
+
     def rec(name, t):
         if acts is not None:
             acts[name] = t
@@ -266,12 +301,13 @@ def to_torch(params, dtype=torch.float32, requires_grad=False):
 
 
 def train_step(X, labels, params, accs, num_layers, root_size, dilated_layers, lr, momentum,
-               dropout_scales=None, dtype=torch.float32, want_acts=False):
+               dropout_scales=None, dtype=torch.float32, want_acts=False, storage=None):
     """One fwd + bwd + momentum update.  Returns (loss, probs, grads, new_params, new_accs, acts)."""
     tp = to_torch(params, dtype, requires_grad=True)
     acts = OrderedDict() if want_acts else None
     Xt = torch.tensor(np.asarray(X), dtype=dtype)
-    logits = forward(Xt, tp, num_layers, root_size, dilated_layers, dropout_scales, acts=acts)
+    logits = forward(Xt, tp, num_layers, root_size, dilated_layers, dropout_scales, acts=acts,
+                     storage=storage)
     loss, probs = loss_and_probs(logits, torch.tensor(np.asarray(labels)))
     if acts is not None:
         for t in acts.values():

@@ -55,9 +55,11 @@ __device__ __forceinline__ void d4_src(int op, int S, int i, int j, int* si, int
   *sj = b;
 }
 
-__global__ void d4_transform_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int S,
+template <typename WordT>
+__global__ void d4_transform_kernel(const WordT* __restrict__ in, WordT* __restrict__ out, int S,
                                     int words, const unsigned char* __restrict__ ops) {
-  extern __shared__ uint32_t tile[];  // [32][32*words + 1]
+  extern __shared__ uint8_t tile_raw[];  // [32][32*words + 1] words
+  WordT* tile = reinterpret_cast<WordT*>(tile_raw);
   const int n = blockIdx.z;
   const int op = ops[n];
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
@@ -69,8 +71,8 @@ __global__ void d4_transform_kernel(const uint32_t* __restrict__ in, uint32_t* _
   const int si0 = min(ci[0], ci[1]), sj0 = min(cj[0], cj[1]);
   const int sh = abs(ci[0] - ci[1]) + 1, sw = abs(cj[0] - cj[1]) + 1;
   const int pitch = 32 * words + 1;
-  const uint32_t* src = in + 1LL * n * S * S * words;
-  uint32_t* dst = out + 1LL * n * S * S * words;
+  const WordT* src = in + 1LL * n * S * S * words;
+  WordT* dst = out + 1LL * n * S * S * words;
   for (int r = threadIdx.y; r < sh; r += blockDim.y)
     for (int w = threadIdx.x; w < sw * words; w += blockDim.x)
       tile[r * pitch + w] = __ldg(src + (1LL * (si0 + r) * S + sj0) * words + w);
@@ -88,14 +90,15 @@ __global__ void d4_transform_kernel(const uint32_t* __restrict__ in, uint32_t* _
 // images.extract_patches (images.py:35-85): patch k of image n sits at column (k / side)*stride,
 // row (k % side)*stride  (x is the OUTER loop in the reference).
 __global__ void extract_patches_kernel(const float* __restrict__ in, int N, int H, int W, int C,
-                                       int P, int stride, int side, float* __restrict__ out) {
+                                       int P, int stride, int side, long long k_begin,
+                                       long long k_count, float* __restrict__ out) {
   const long long row_elems = 1LL * P * C;
-  const long long total = 1LL * N * side * side * P * row_elems;
+  const long long total = k_count * P * row_elems;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
        i += 1LL * gridDim.x * blockDim.x) {
     const int xc = static_cast<int>(i % row_elems);
     const int py = static_cast<int>((i / row_elems) % P);
-    const long long k_all = i / (row_elems * P);
+    const long long k_all = k_begin + i / (row_elems * P);
     const int k = static_cast<int>(k_all % (side * side));
     const int n = static_cast<int>(k_all / (side * side));
     const int x0 = (k / side) * stride, y0 = (k % side) * stride;
@@ -106,8 +109,12 @@ __global__ void extract_patches_kernel(const float* __restrict__ in, int N, int 
 // images.images_from_patches (images.py:131-164) in gather form: every output pixel sums the
 // patches covering it in the reference's order (x outer, y inner) in fp64 and divides by the
 // hit count -- deterministic, no atomics.
+// k_lo/k_hi restrict the sum to patches whose global index (n*side*side + k) lies in
+// [k_lo, k_hi) -- a rank of a sharded prediction holds only that slice (patches points at patch
+// k_lo) and emits partial sums (normalize = 0) that are added and divided after the gather.
 __global__ void overlap_average_kernel(const float* __restrict__ patches, int N, int side, int P,
-                                       int C, int stride, int S, float* __restrict__ out) {
+                                       int C, int stride, int S, long long k_lo, long long k_hi,
+                                       int normalize, float* __restrict__ out) {
   const long long row_elems = 1LL * S * C;
   const long long total = 1LL * N * S * row_elems;
   const long long patch_elems = 1LL * P * P * C;
@@ -123,13 +130,16 @@ __global__ void overlap_average_kernel(const float* __restrict__ patches, int N,
     if (y - P + 1 <= 0) ky_lo = 0;
     const int kx_hi = min(x / stride, side - 1), ky_hi = min(y / stride, side - 1);
     double acc = 0.0;
-    const float* base = patches + 1LL * n * side * side * patch_elems;
+    const long long img_k0 = 1LL * n * side * side;
     for (int kx = kx_lo; kx <= kx_hi; ++kx)
-      for (int ky = ky_lo; ky <= ky_hi; ++ky)
-        acc += static_cast<double>(__ldg(base + (1LL * (kx * side + ky)) * patch_elems +
+      for (int ky = ky_lo; ky <= ky_hi; ++ky) {
+        const long long k = img_k0 + kx * side + ky;
+        if (k < k_lo || k >= k_hi) continue;
+        acc += static_cast<double>(__ldg(patches + (k - k_lo) * patch_elems +
                                          (1LL * (y - ky * stride) * P + (x - kx * stride)) * C + c));
+      }
     const int cnt = (kx_hi - kx_lo + 1) * (ky_hi - ky_lo + 1);
-    out[i] = static_cast<float>(acc / static_cast<double>(cnt));
+    out[i] = static_cast<float>(normalize ? acc / static_cast<double>(cnt) : acc);
   }
 }
 
@@ -152,8 +162,10 @@ __global__ void rotate_nn_crop_kernel(const float* __restrict__ in, int N, int H
     const int y = static_cast<int>((i / row_elems) % crop);
     const int n = static_cast<int>(i / (row_elems * crop));
     const double oy = static_cast<double>(y + rp.crop0), ox = static_cast<double>(x + rp.crop0);
-    const double iy = rp.m00 * oy + rp.m01 * ox + rp.off0;
-    const double ix = rp.m10 * oy + rp.m11 * ox + rp.off1;
+    // SciPy's NI_GeometricTransform order: cc = shift; cc += o[0]*m[i][0]; cc += o[1]*m[i][1]
+    // (explicit _rn intrinsics: no FMA contraction, so ties resolve exactly as on the CPU)
+    const double iy = __dadd_rn(__dadd_rn(rp.off0, __dmul_rn(oy, rp.m00)), __dmul_rn(ox, rp.m01));
+    const double ix = __dadd_rn(__dadd_rn(rp.off1, __dmul_rn(oy, rp.m10)), __dmul_rn(ox, rp.m11));
     const long long ry = static_cast<long long>(floor(iy + 0.5));
     const long long rx = static_cast<long long>(floor(ix + 0.5));
     float v = 0.f;
@@ -204,70 +216,74 @@ int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* 
 
 int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
                      const unsigned char* ops, void* stream) {
-  if (N < 1 || S < 1 || pixel_bytes < 4 || pixel_bytes % 4)
-    return set_error(RSU_EINVAL, "d4_transform: pixel_bytes %d must be a multiple of 4", pixel_bytes);
+  if (N < 1 || S < 1 || pixel_bytes < 1)
+    return set_error(RSU_EINVAL, "d4_transform: bad shape N=%d S=%d pixel_bytes=%d", N, S, pixel_bytes);
   if (in == out) return set_error(RSU_EINVAL, "d4_transform: in-place not supported");
-  const int words = pixel_bytes / 4;
-  const size_t smem = 32 * (32 * words + 1) * sizeof(uint32_t);
-  if (smem > 48 * 1024) return set_error(RSU_EINVAL, "d4_transform: pixel too large");
-  dim3 grid((S + 31) / 32, (S + 31) / 32, N), block(32, 8);
   if (N > 65535) return set_error(RSU_EINVAL, "d4_transform: N > 65535");
-  d4_transform_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(
-      static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, words, ops);
+  dim3 grid((S + 31) / 32, (S + 31) / 32, N), block(32, 8);
+  const bool word4 = pixel_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+  if (word4) {
+    const int words = pixel_bytes / 4;
+    const size_t smem = 32 * (32 * words + 1) * sizeof(uint32_t);
+    if (smem > 48 * 1024) return set_error(RSU_EINVAL, "d4_transform: pixel too large");
+    d4_transform_kernel<uint32_t><<<grid, block, smem, (cudaStream_t)stream>>>(
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, words, ops);
+  } else {  // byte-granular pixels (uint8 label masks)
+    const size_t smem = 32 * (32 * pixel_bytes + 1);
+    if (smem > 48 * 1024) return set_error(RSU_EINVAL, "d4_transform: pixel too large");
+    d4_transform_kernel<uint8_t><<<grid, block, smem, (cudaStream_t)stream>>>(
+        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, pixel_bytes, ops);
+  }
   return check_launch("d4_transform");
 }
 
 int rsu_extract_patches(const float* in, int N, int H, int W, int C, int patch, int stride,
-                        float* out, void* stream) {
+                        long long k_begin, long long k_count, float* out, void* stream) {
   if (H != W) return set_error(RSU_EINVAL, "extract_patches: Assume square images");
   if (stride < 1 || patch > H || (H - patch) % stride != 0)
     return set_error(RSU_EINVAL, "extract_patches: Stride sliding should cover the whole image");
   const int side = (H - patch) / stride + 1;
-  const long long total = 1LL * N * side * side * patch * patch * C;
+  const long long all = 1LL * N * side * side;
+  if (k_count < 0) k_count = all - k_begin;
+  if (k_begin < 0 || k_begin + k_count > all || k_count < 1)
+    return set_error(RSU_EINVAL, "extract_patches: patch range [%lld, +%lld) outside %lld", k_begin,
+                     k_count, all);
+  const long long total = k_count * patch * patch * C;
   extract_patches_kernel<<<geo_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      in, N, H, W, C, patch, stride, side, out);
+      in, N, H, W, C, patch, stride, side, k_begin, k_count, out);
   return check_launch("extract_patches");
 }
 
-int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int stride, float* out,
+int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int stride,
+                        long long k_begin, long long k_count, int normalize, float* out,
                         void* stream) {
   if (N < 1 || side < 1 || P < 1 || C < 1 || stride < 1)
     return set_error(RSU_EINVAL, "overlap_average: shape");
+  const long long all = 1LL * N * side * side;
+  if (k_count < 0) k_count = all - k_begin;
+  if (k_begin < 0 || k_begin + k_count > all)
+    return set_error(RSU_EINVAL, "overlap_average: patch range outside [0, %lld)", all);
   const int S = (side - 1) * stride + P;
   const long long total = 1LL * N * S * S * C;
   overlap_average_kernel<<<geo_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      patches, N, side, P, C, stride, S, out);
+      patches, N, side, P, C, stride, S, k_begin, k_begin + k_count, normalize, out);
   return check_launch("overlap_average");
 }
 
-int rsu_rotate_nn_crop(const float* in, int N, int H, int C, double cos_a, double sin_a, int crop,
-                       float* out, void* stream) {
-  if (crop % 2 != 0) return set_error(RSU_EINVAL, "rotate_nn_crop: crop must be even");
-  // scipy.ndimage.rotate(reshape=True): see oracle/images_oracle.py::rotate_nn for the derivation
-  const double c = cos_a, s = sin_a;
-  // output bounding box of the rotated HxH image
-  const double iy[4] = {0, 0, (double)H, (double)H}, ix[4] = {0, (double)H, (double)H, 0};
-  double miny = 1e300, maxy = -1e300, minx = 1e300, maxx = -1e300;
-  for (int k = 0; k < 4; ++k) {
-    const double oy = c * iy[k] + s * ix[k], ox = -s * iy[k] + c * ix[k];
-    miny = oy < miny ? oy : miny;
-    maxy = oy > maxy ? oy : maxy;
-    minx = ox < minx ? ox : minx;
-    maxx = ox > maxx ? ox : maxx;
-  }
-  const int out_h = static_cast<int>((maxy - miny) + 0.5), out_w = static_cast<int>((maxx - minx) + 0.5);
-  if (out_h != out_w) return set_error(RSU_EINVAL, "rotate_nn_crop: non-square output");
-  if (crop > out_h) return set_error(RSU_EINVAL, "rotate_nn_crop: crop %d > rotated %d", crop, out_h);
+int rsu_rotate_nn_crop(const float* in, int N, int H, int C, const double* matrix_host,
+                       const double* offset_host, int crop0, int crop, float* out, void* stream) {
+  if (N < 1 || H < 1 || C < 1 || crop < 1 || crop0 < 0)
+    return set_error(RSU_EINVAL, "rotate_nn_crop: shape");
   RotParams rp;
-  rp.m00 = c;
-  rp.m01 = s;
-  rp.m10 = -s;
-  rp.m11 = c;
-  const double in_c = (H - 1) / 2.0, out_c = (out_h - 1) / 2.0;
-  rp.off0 = in_c - (c * out_c + s * out_c);
-  rp.off1 = in_c - (-s * out_c + c * out_c);
-  rp.out_side = out_h;
-  rp.crop0 = out_h / 2 - crop / 2;
+  rp.m00 = matrix_host[0];
+  rp.m01 = matrix_host[1];
+  rp.m10 = matrix_host[2];
+  rp.m11 = matrix_host[3];
+  rp.off0 = offset_host[0];
+  rp.off1 = offset_host[1];
+  rp.out_side = 0;
+  rp.crop0 = crop0;
   const long long total = 1LL * N * crop * crop * C;
   rotate_nn_crop_kernel<<<geo_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, N, H, C, rp, crop,
                                                                                out);

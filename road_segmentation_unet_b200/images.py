@@ -1,0 +1,288 @@
+"""IMAGES -- host-side mirror of the reference's src/images.py geometry helpers.
+
+Same function names, argument names/orders/defaults, assertions and output dtypes as the
+reference (NumPy in, NumPy out), but every function runs a hand-written CUDA kernel of
+librsu_b200.so (csrc/geometry.cu).  The `*_dev` variants take / return torch CUDA tensors so the
+prediction pipeline (tf_aerial_images.ConvolutionalModel.predict) chains them without leaving
+the GPU.  Pure data movement (mirror, flips, rot90, crops, patches, nearest-neighbour rotation)
+is bit-exact for float32 and float64 inputs (float64 moves as pairs of 32-bit words); the two
+averaging helpers accumulate in fp64 on the device from fp32 inputs.
+
+The I/O and visualisation helpers of the reference (load, overlays, save_all, ...) are out of
+scope; the small NumPy post-processing rules needed to score a prediction
+(quantize_mask, labels_for_patches, img_float_to_uint8, predictions_to_patches) are kept as host
+code.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+from .constants import PIXEL_DEPTH, FOREGROUND_THRESHOLD
+
+
+# ------------------------------------------------------------------ plumbing
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _as_words(arr):
+    """NumPy array -> (float32 device tensor [N,H,W,Cw], restore) where float64 travels as two
+    32-bit words per element so that pure data movement stays bit-exact."""
+    arr = np.ascontiguousarray(arr)
+    if arr.dtype not in (np.float32, np.float64):
+        arr = arr.astype(np.float64)
+    dt = arr.dtype
+    a4 = arr if arr.ndim == 4 else arr[..., None]
+    words = a4.view(np.float32) if dt == np.float64 else a4
+    t = torch.from_numpy(np.ascontiguousarray(words)).cuda()
+
+    def restore(out_t, squeeze):
+        o = out_t.cpu().numpy()
+        if dt == np.float64:
+            o = o.view(np.float64)
+        return o[..., 0] if squeeze else o
+
+    return t, restore, arr.ndim == 3
+
+
+# ------------------------------------------------------------------ device-level helpers
+def mirror_border_dev(x, n):
+    """x: float32 CUDA [N,H,W,C] -> [N,H+2n,W+2n,C] (np.pad 'symmetric', images.py:269-281)."""
+    N, H, W, Cc = x.shape
+    out = torch.empty(N, H + 2 * n, W + 2 * n, Cc, dtype=torch.float32, device=x.device)
+    call("rsu_mirror_pad", _ptr(x), N, H, W, Cc, int(n), _ptr(out))
+    return out
+
+
+def d4_transform_dev(x, ops_u8):
+    """Per-image dihedral transform: out[i] = rot90(flipud(x[i]) if op&4 else x[i], k=op&3)."""
+    N, S = x.shape[0], x.shape[1]
+    assert x.shape[2] == S, "square images required"
+    pixel_bytes = x.element_size() * (x.shape[3] if x.dim() == 4 else 1)
+    out = torch.empty_like(x)
+    call("rsu_d4_transform", _ptr(x), _ptr(out), N, S, pixel_bytes, _ptr(ops_u8))
+    return out
+
+
+ENSEMBLE_OPS = (0, 4 | 2, 4, 1, 2, 3)  # orig, fliplr, flipud, rot90 k=1,2,3  (images.py:376-396)
+
+
+def image_augmentation_ensemble_dev(x):
+    n = x.shape[0]
+    rep = x.repeat(6, 1, 1, 1)
+    ops_t = torch.tensor([op for op in ENSEMBLE_OPS for _ in range(n)], dtype=torch.uint8, device=x.device)
+    return d4_transform_dev(rep, ops_t)
+
+
+def extract_patches_dev(x, patch_size, stride, k_begin=0, k_count=-1, out=None):
+    N, H, W, Cc = x.shape
+    side = (H - patch_size) // stride + 1
+    total = N * side * side
+    cnt = total - k_begin if k_count < 0 else k_count
+    if out is None:
+        out = torch.empty(cnt, patch_size, patch_size, Cc, dtype=torch.float32, device=x.device)
+    call("rsu_extract_patches", _ptr(x), N, H, W, Cc, int(patch_size), int(stride), int(k_begin),
+         int(cnt), _ptr(out))
+    return out
+
+
+def images_from_patches_dev(patches, num_images, side, stride, k_begin=0, k_count=-1, normalize=True):
+    """patches: float32 CUDA [k_count, P, P, C] (slice of the patch list starting at k_begin)."""
+    P, Cc = patches.shape[1], patches.shape[3]
+    S = (side - 1) * stride + P
+    out = torch.empty(num_images, S, S, Cc, dtype=torch.float32, device=patches.device)
+    call("rsu_overlap_average", _ptr(patches), num_images, side, P, Cc, int(stride), int(k_begin),
+         int(k_count), int(bool(normalize)), _ptr(out))
+    return out
+
+
+def invert_image_augmentation_ensemble_dev(masks):
+    """masks: float32 CUDA [6N,S,S] (or [6N,S,S,1]) -> [N,S,S]."""
+    assert masks.shape[0] % 6 == 0
+    n, S = masks.shape[0] // 6, masks.shape[1]
+    out = torch.empty(n, S, S, dtype=torch.float32, device=masks.device)
+    call("rsu_ensemble_invert", _ptr(masks.contiguous()), n, S, _ptr(out))
+    return out
+
+
+def _cos_sin_deg(angle):
+    try:  # SciPy evaluates the rotation matrix with cosdg / sindg (exact at multiples of 90)
+        from scipy import special
+        return float(special.cosdg(angle)), float(special.sindg(angle))
+    except Exception:  # pragma: no cover
+        import math
+        return math.cos(math.radians(angle)), math.sin(math.radians(angle))
+
+
+def rotation_geometry(side, angle):
+    """scipy.ndimage.rotate(reshape=True) geometry for a side x side plane: (matrix, offset,
+    out_side), evaluated with the same NumPy expressions SciPy uses."""
+    c, s = _cos_sin_deg(angle)
+    rot = np.array([[c, s], [-s, c]])
+    out_bounds = rot @ np.array([[0, 0, side, side], [0, side, 0, side]], dtype=np.float64)
+    out_shape = (np.ptp(out_bounds, axis=1) + 0.5).astype(int)
+    out_center = rot @ ((out_shape - 1) / 2)
+    in_center = (np.array([side, side]) - 1) / 2
+    return rot, in_center - out_center, int(out_shape[0])
+
+
+def rotate_crop_dev(x, angle, crop=None):
+    """crop_imgs(rotate_imgs(x, angle), crop) on float32 CUDA [N,H,H,C]; only the centre crop of
+    the rotated image is produced (crop=None: the whole rotated image)."""
+    N, H, _, Cc = x.shape
+    rot, offset, side = rotation_geometry(H, angle)
+    if crop is None:
+        crop0, crop = 0, side
+    else:
+        assert side >= crop and crop % 2 == 0
+        crop0 = int(side / 2) - crop // 2
+    out = torch.empty(N, crop, crop, Cc, dtype=torch.float32, device=x.device)
+    m = (C.c_double * 4)(rot[0, 0], rot[0, 1], rot[1, 0], rot[1, 1])
+    o = (C.c_double * 2)(offset[0], offset[1])
+    call("rsu_rotate_nn_crop", _ptr(x), N, H, Cc, m, o, crop0, int(crop), _ptr(out))
+    return out
+
+
+# ------------------------------------------------------------------ reference API (NumPy)
+def img_float_to_uint8(img):
+    """Transform an array of float images into uint8 images"""
+    return (img * PIXEL_DEPTH).round().astype(np.uint8)
+
+
+def mirror_border(images, n):
+    """mirrors border n border pixels on each side and corner (images.py:269-281)"""
+    t, restore, squeeze = _as_words(images)
+    return restore(mirror_border_dev(t, n), squeeze)
+
+
+def extract_patches(images, patch_size, stride=None, predict_patch_size=None):
+    """extract square patches from a batch of images (images.py:35-85); float64 output"""
+    if not predict_patch_size:
+        predict_patch_size = patch_size
+
+    assert (patch_size - predict_patch_size) % 2 == 0 and predict_patch_size <= patch_size
+
+    if not stride:
+        stride = patch_size
+
+    num_images, image_height, image_width = images.shape[:3]
+    assert image_height == image_width, "Assume square images"
+    assert (image_height - patch_size) % stride == 0, "Stride sliding should cover the whole image"
+
+    t, restore, squeeze = _as_words(images)
+    out = restore(extract_patches_dev(t, patch_size, stride), squeeze)
+    return out.astype(np.float64, copy=False)
+
+
+def images_from_patches(patches, stride=None):
+    """Transform a list of patches into images, averaging overlaps (images.py:131-164)"""
+    num_images, num_patches, patch_size, _, num_channel = patches.shape
+
+    if stride is None:
+        stride = patch_size
+
+    num_patches_side = int(np.sqrt(num_patches))
+    assert np.sqrt(num_patches) == num_patches_side, "Square image assumption broken"
+
+    p = torch.from_numpy(np.ascontiguousarray(patches, dtype=np.float32)).cuda()
+    p = p.view(num_images * num_patches, patch_size, patch_size, num_channel)
+    out = images_from_patches_dev(p, num_images, num_patches_side, stride)
+    return out.cpu().numpy().astype(np.float64)
+
+
+def rotate_imgs(imgs, angle):
+    """safeguard to avoid useless rotation by 0 (images.py:313-317)"""
+    if angle == 0:
+        return imgs
+    t, restore, squeeze = _as_words(imgs)
+    return restore(rotate_crop_dev(t, angle), squeeze)
+
+
+def crop_imgs(imgs, crop_size):
+    """centre crop (images.py:354-373) -- a view, like the reference"""
+    batch_size, height, width = imgs.shape[:3]
+    assert height == width and height >= crop_size
+    assert crop_size % 2 == 0
+    half_crop = int(crop_size / 2)
+    center = int(height / 2)
+    return imgs[:, center - half_crop:center + half_crop, center - half_crop:center + half_crop]
+
+
+def expand_and_rotate(imgs, angles, offset=0):
+    """rotate some images by an angle, mirror image for missing part and expanding to output_size
+    (images.py:320-351); angle-major float64 output"""
+    has_channels = (len(imgs.shape) == 4)
+    if not has_channels:
+        imgs = np.expand_dims(imgs, -1)
+
+    batch_size, height, width, num_channel = imgs.shape
+    assert height == width
+
+    output_size = height + 2 * offset
+    padding = int(np.ceil(height * (np.sqrt(2) - 1) / 2)) + int(np.ceil(offset / np.sqrt(2)))
+
+    print("Applying rotations: {} degrees... ".format(", ".join([str(a) for a in angles])))
+    t, restore, _ = _as_words(imgs)
+    padded = mirror_border_dev(t, padding)
+    outs = []
+    for angle in angles:
+        if angle == 0:
+            c0 = int(padded.shape[1] / 2) - output_size // 2
+            assert output_size % 2 == 0
+            outs.append(padded[:, c0:c0 + output_size, c0:c0 + output_size].contiguous())
+        else:
+            outs.append(rotate_crop_dev(padded, angle, output_size))
+    rotated_imgs = restore(torch.cat(outs, dim=0), False).astype(np.float64, copy=False)
+    print("Done")
+
+    if not has_channels:
+        rotated_imgs = np.squeeze(rotated_imgs, -1)
+
+    return rotated_imgs
+
+
+def image_augmentation_ensemble(imgs):
+    """create ensemble of images to be predicted (images.py:376-396); float64 [6N,H,W,C]"""
+    t, restore, squeeze = _as_words(imgs)
+    return restore(image_augmentation_ensemble_dev(t), squeeze).astype(np.float64, copy=False)
+
+
+def invert_image_augmentation_ensemble(masks):
+    """assemble masks of prediction images created by `image_augmentation_ensemble`
+    (images.py:399-417).  Unlike the reference the argument is not modified in place."""
+    assert masks.shape[0] % 6 == 0
+    m = np.ascontiguousarray(masks, dtype=np.float32)
+    has_c = m.ndim == 4
+    assert not has_c or m.shape[3] == 1, "masks have one channel"
+    t = torch.from_numpy(m.reshape(m.shape[0], m.shape[1], m.shape[2])).cuda()
+    out = invert_image_augmentation_ensemble_dev(t).cpu().numpy().astype(np.float64)
+    return out[..., None] if has_c else out
+
+
+# ------------------------------------------------------------------ host-side scoring rules
+def labels_for_patches(patches):
+    """label 1 = road when the patch mean exceeds FOREGROUND_THRESHOLD (images.py:88-99)"""
+    foreground = patches.mean(axis=(1, 2)) > FOREGROUND_THRESHOLD
+    return foreground.astype(np.int64)
+
+
+def predictions_to_patches(predictions, patch_size):
+    """Expand each prediction to a square patch (images.py:167-180)"""
+    num_predictions = predictions.shape[0]
+    predictions = np.resize(predictions, (num_predictions, 1, 1, 1))
+    return np.broadcast_to(predictions, (num_predictions, patch_size, patch_size, 1))
+
+
+def quantize_mask(masks, threshold, patch_size):
+    """patch_size x patch_size vote: mean(prob >= 0.5) > threshold (images.py:256-266)"""
+    num_images, img_size, _, _ = masks.shape
+    quantized_masks = masks.copy()
+    for n in range(num_images):
+        for y in range(0, img_size, patch_size):
+            for x in range(0, img_size, patch_size):
+                label = (masks[n, y:y + patch_size, x:x + patch_size, 0] >= 0.5).mean() > threshold
+                quantized_masks[n, y:y + patch_size, x:x + patch_size, 0] = label
+    return quantized_masks

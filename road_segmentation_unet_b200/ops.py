@@ -18,6 +18,42 @@ from . import _lib
 from ._lib import ConvGemmDesc, View, WgradDesc, call, view
 
 
+# ------------------------------------------------------------------ optional kernel timing
+# bench.py brackets the two tcgen05 kernels with CUDA events on the launching stream to report
+# the roofline of the dominant kernel; the engine tags every layer with its algorithmic FLOPs.
+_PROFILE = None
+_LAYER = (None, 0.0)
+
+
+def set_layer(name, flops):
+    global _LAYER
+    _LAYER = (name, float(flops))
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_stop():
+    """Returns [(kind, layer, alg_flops, milliseconds)] and disables profiling."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    return [(k, n, f, e0.elapsed_time(e1)) for (k, n, f, e0, e1) in rec]
+
+
+def _timed(kind, fn, *args):
+    if _PROFILE is None:
+        return fn(*args)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(*args)
+    e1.record()
+    _PROFILE.append((kind, _LAYER[0], _LAYER[1], e0, e1))
+
+
 def _taps(desc, taps):
     desc.n_taps = len(taps)
     for i, (dy, dx) in enumerate(taps):
@@ -59,7 +95,7 @@ def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None,
         d.mask = _ptr(mask)
         d.mask_sn, d.mask_sy, d.mask_sx = mask.stride()[:3]
     d.accumulate = int(accumulate)
-    call("rsu_conv_gemm", C.byref(d))
+    _timed("conv_gemm", call, "rsu_conv_gemm", C.byref(d))
 
 
 def wgrad_gemm(srcs, taps, grad, grad_off, out, grid_hw):
@@ -78,7 +114,7 @@ def wgrad_gemm(srcs, taps, grad, grad_off, out, grid_hw):
     d.N_img = g.N
     d.out = _ptr(out)
     d.ldo = out.stride(0)
-    call("rsu_wgrad_gemm", C.byref(d))
+    _timed("wgrad_gemm", call, "rsu_wgrad_gemm", C.byref(d))
 
 
 # ------------------------------------------------------------------ weight packing

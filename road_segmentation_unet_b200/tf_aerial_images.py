@@ -1,0 +1,490 @@
+"""Train / predict loop -- host-side mirror of the reference's src/tf_aerial_images.py.
+
+Keeps the reference's flag names and defaults (tf_aerial_images.py:15-46), `Options` (:51-84) and
+`ConvolutionalModel(options, session)` with `.train`, `.predict`, `.predict_batchwise`, `.save`,
+`.restore`, `.input_size`, `.experiment_name` (:87-379).  `session` has no TensorFlow meaning any
+more and is accepted and ignored.  One process drives one GPU; under torchrun (WORLD_SIZE > 1,
+`--num_gpu` = world size) training is data parallel with one bucketed NCCL all-reduce of the flat
+gradient per step, overlapped with the remaining backward kernels, and prediction shards the
+patch list across ranks with a single final reduction of the per-rank partial mask sums.
+"""
+import argparse
+import glob
+import os
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from . import images
+from . import unet
+from .constants import NUM_CHANNELS, IMG_PATCH_SIZE, FOREGROUND_THRESHOLD
+
+
+# ------------------------------------------------------------------ flags (names/defaults verbatim)
+def _bool(v):
+    if isinstance(v, bool):
+        return v
+    return str(v).lower() in ("1", "true", "t", "yes", "y")
+
+
+FLAG_DEFS = [
+    ("batch_size", int, 25, "Batch size of training instances"),
+    ("dilated_layers", _bool, False, "Add dilated CNN layers"),
+    ("dropout", float, 0.8, "Probability to keep an input"),
+    ("ensemble_prediction", _bool, False, "Ensemble Prediction"),
+    ("eval_data_dir", str, None, "Directory containing eval images"),
+    ("eval_every", int, 500, "Number of steps between evaluations"),
+    ("eval_train", _bool, False, "Evaluate training data"),
+    ("gpu", int, -1, "GPU to run the model on"),
+    ("image_augmentation", _bool, False, "Augment training set of images with transformations"),
+    ("interactive", _bool, False, "Spawn interactive Tensorflow session"),
+    ("logdir", str, os.path.abspath("./logdir"), "Directory where to write logfiles"),
+    ("lr", float, 0.01, "Initial learning rate"),
+    ("model_path", str, None, "Restore exact model path"),
+    ("momentum", float, 0.9, "Momentum"),
+    ("num_epoch", int, 5, "Number of pass on the dataset during training"),
+    ("num_eval_images", int, 4, "Number of images to predict for an evaluation"),
+    ("num_gpu", int, 1, "Number of available GPUs to run the model on"),
+    ("num_layers", int, 5, "Number of layers of the U-Net"),
+    ("patch_size", int, 128, "Size of the prediction image"),
+    ("pred_batch_size", int, 2, "Batch size of batchwise prediction"),
+    ("restore_date", str, None, "Restore the model from specific date"),
+    ("restore_epoch", int, None, "Restore the model from specific epoch"),
+    ("restore_model", _bool, False, "Restore the model from previous checkpoint"),
+    ("root_size", int, 64, "Number of filters of the first U-Net layer"),
+    ("rotation_angles", str, None, "Rotation angles"),
+    ("save_path", str, os.path.abspath("./runs"),
+     "Directory where to write checkpoints, overlays and submissions"),
+    ("seed", int, 2017, "Random seed for reproducibility"),
+    ("stride", int, 16, "Sliding delta for patches"),
+    ("train_data_dir", str, os.path.abspath("./data/training"),
+     "Directory containing training images/ groundtruth/"),
+    ("train_score_every", int, 1000, "Compute training score after the given number of iterations"),
+]
+
+
+def make_parser():
+    p = argparse.ArgumentParser(description="B200 U-Net road segmentation (reference flag surface)")
+    for name, typ, default, helptext in FLAG_DEFS:
+        if typ is _bool:
+            p.add_argument("--" + name, type=_bool, nargs="?", const=True, default=default, help=helptext)
+        else:
+            p.add_argument("--" + name, type=typ, default=default, help=helptext)
+    return p
+
+
+FLAGS = make_parser().parse_args([])
+
+
+class Options(object):
+    """Options used by our model (tf_aerial_images.py:51-84)."""
+
+    def __init__(self, flags=None):
+        f = flags if flags is not None else FLAGS
+        for name, _, _, _ in FLAG_DEFS:
+            setattr(self, name, getattr(f, name))
+        self.rotation_angles = None if not f.rotation_angles else \
+            [int(i) for i in str(f.rotation_angles).split(",")]
+
+
+# ------------------------------------------------------------------ distributed plumbing
+class _Dist:
+    """torch.distributed (NCCL) as plumbing: rank / world from the torchrun environment."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.active = self.world > 1
+        if self.active:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+                dist.init_process_group(backend=backend)
+            self.dist = dist
+        self.comm_stream = None
+
+    def barrier(self):
+        if self.active:
+            self.dist.barrier()
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous slice [k0, k1) of a work list owned by `rank` (prediction patches)."""
+    return n_items * rank // world, n_items * (rank + 1) // world
+
+
+def rank_batch_indices(indices, offset, rank, batch_size):
+    """The slice of the (identically shuffled) epoch permutation that `rank` trains on at the
+    global step starting at `offset`: ranks take consecutive batch_size-sized pieces."""
+    lo = offset + rank * batch_size
+    return indices[lo:lo + batch_size]
+
+
+class GradientAllReducer:
+    """Bucketed all-reduce (sum) of the flat gradient, overlapped with the backward pass: as soon
+    as a block's weight gradients are complete its slice is reduced on a side stream.  finish()
+    waits for all buckets and returns the 1/world factor the optimizer applies (mean gradient =
+    gradient of the global-batch mean loss, tf_aerial_images.py:108)."""
+
+    def __init__(self, dist_module, world, flat_grads):
+        self.dist = dist_module
+        self.world = world
+        self.g = flat_grads
+        self.cuda = flat_grads.is_cuda
+        self.stream = torch.cuda.Stream() if self.cuda else None
+        self.pending = []
+        self.reduced = []
+
+    def bucket_ready(self, start, end):
+        self.reduced.append((start, end))
+        if not self.cuda:
+            self.pending.append(self.dist.all_reduce(self.g[start:end], async_op=True))
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self.pending.append(self.dist.all_reduce(self.g[start:end], async_op=True))
+
+    def finish(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        self.reduced = []
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        return 1.0 / self.world
+
+
+# ------------------------------------------------------------------ the model
+class ConvolutionalModel:
+    def __init__(self, options, session=None):
+        self._options = options
+        self._session = session  # accepted for signature parity, unused
+
+        np.random.seed(options.seed)
+        self.input_size = unet.input_size_needed(options.patch_size, options.num_layers)
+
+        self.experiment_name = datetime.now().strftime("%Y-%m-%dT%Hh%Mm%Ss")
+        self._dist = _Dist()
+        if torch.cuda.is_available():
+            torch.cuda.set_device(self._dist.local_rank if self._dist.active else
+                                  (options.gpu if options.gpu >= 0 else 0))
+        self._aug_rng = np.random.RandomState(options.seed + 7919 * self._dist.rank)
+        self.scalars = []  # (step, loss, lr): what the reference sends to TensorBoard
+        self.build_graph()
+
+    # -- "graph": the planned engine --------------------------------------------------------
+    def build_graph(self):
+        opts = self._options
+        self._net = unet.UNet(opts.num_layers, opts.root_size, opts.dilated_layers, opts.batch_size,
+                              self.input_size, seed=opts.seed, training=True)
+        B, S, P = opts.batch_size, self.input_size, opts.patch_size
+        assert self._net.P == P
+        self._h_patches = torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32).pin_memory()
+        self._h_labels = torch.empty(B, P, P, dtype=torch.uint8).pin_memory()
+        self._d_patches = torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+        self._d_labels = torch.empty(B, P, P, dtype=torch.uint8, device="cuda")
+        self._h_probs = torch.empty(B, P, P, dtype=torch.float32).pin_memory()
+        self._reducer = GradientAllReducer(self._dist.dist, self._dist.world, self._net.grads) \
+            if self._dist.active else None
+        if self._reducer is not None:
+            self._net.on_bucket_ready = self._reducer.bucket_ready
+
+    @property
+    def net(self):
+        return self._net
+
+    @property
+    def global_step(self):
+        return self._net.global_step
+
+    # -- in-graph augmentation (tf_aerial_images.py:173-210) ---------------------------------
+    def stochastic_images_augmentation(self, imgs, masks):
+        """Per sample: flip_up_down applied by each of three fair coins (the reference hard-codes
+        flip_up_down at :188), then rot90 by floor(4U): a uniform element of the dihedral group.
+        imgs [B,S,S,3] fp32 / masks [B,P,P] uint8 device tensors."""
+        B = imgs.shape[0]
+        coins = self._aug_rng.random_sample((3, B)) > 0.5
+        flip = coins[0] ^ coins[1] ^ coins[2]
+        k = np.floor(self._aug_rng.random_sample(B) * 4).astype(np.int64)
+        ops_np = (flip.astype(np.uint8) << 2) | k.astype(np.uint8)
+        ops_t = torch.from_numpy(ops_np).cuda()
+        return images.d4_transform_dev(imgs, ops_t), images.d4_transform_dev(masks, ops_t)
+
+    # -- one training step on host batches ---------------------------------------------------
+    def train_batch(self, patches_batch, labels_batch):
+        """patches_batch [B,S,S,3], labels_batch [B,P,P] (host arrays).  Returns (loss, probs)."""
+        opts = self._options
+        net = self._net
+        if torch.is_tensor(patches_batch) and patches_batch.is_pinned():
+            # caller already staged the batch in pinned host memory (fp32 patches, uint8 labels)
+            self._d_patches.copy_(patches_batch, non_blocking=True)
+            self._d_labels.copy_(labels_batch, non_blocking=True)
+        else:
+            self._h_patches.copy_(torch.from_numpy(np.ascontiguousarray(patches_batch, dtype=np.float32)))
+            self._h_labels.copy_(torch.from_numpy(np.ascontiguousarray(labels_batch).astype(np.uint8)))
+            self._d_patches.copy_(self._h_patches, non_blocking=True)
+            self._d_labels.copy_(self._h_labels, non_blocking=True)
+        x, y = self._d_patches, self._d_labels
+        if opts.image_augmentation:
+            x, y = self.stochastic_images_augmentation(x, y)
+        lr = net.learning_rate(opts.lr)
+        net.grads.zero_()
+        net.forward(x, y, keep=opts.dropout)
+        net.backward()
+        scale = self._reducer.finish() if self._reducer is not None else 1.0
+        net.apply_gradients(opts.lr, opts.momentum, scale)
+        self._h_probs.copy_(net.probs, non_blocking=True)
+        loss = float(net.loss.item())  # synchronises: loss and probabilities are fetched every step
+        if self._dist.active:
+            t = torch.tensor([loss], device="cuda")
+            self._dist.dist.all_reduce(t)
+            loss = float(t.item()) / self._dist.world
+        self.scalars.append((net.global_step, loss, lr))
+        return loss, self._h_probs.numpy()
+
+    def train(self, patches, labels_patches, imgs, labels):
+        """Train the model for one epoch (tf_aerial_images.py:212-269)."""
+        opts = self._options
+        world, rank = self._dist.world, self._dist.rank
+
+        labels_patches = (labels_patches >= 0.5) * 1.
+        labels = (labels >= 0.5) * 1.
+
+        num_train_patches = patches.shape[0]
+
+        indices = np.arange(0, num_train_patches)
+        np.random.shuffle(indices)
+
+        num_errors = 0
+        total = 0
+        gb = opts.batch_size * world  # global batch: every rank takes its own slice of it
+        for batch_i, offset in enumerate(range(0, num_train_patches - gb, gb)):
+            batch_indices = rank_batch_indices(indices, offset, rank, opts.batch_size)
+            l, predictions = self.train_batch(patches[batch_indices, :, :, :], labels_patches[batch_indices])
+            step = self._net.global_step
+            print("Batch {} Step {}".format(batch_i, step), end="\r")
+
+            num_errors += np.abs(labels_patches[batch_indices] - predictions).sum()
+            total += opts.batch_size
+            self.misclassification = (num_errors, total)
+
+            # from time to time do full prediction on some images
+            if step > 0 and step % opts.eval_every == 0:
+                print()
+                images_to_predict = imgs[:opts.num_eval_images, :, :, :]
+                self.last_eval_masks = self.predict(images_to_predict)
+
+            if step > 0 and step % opts.train_score_every == 0:
+                self.last_train_masks = self.predict(imgs)
+
+    # -- sliding-window prediction (tf_aerial_images.py:271-328) -----------------------------
+    def predict(self, imgs):
+        """Run inference on `imgs` and return predicted masks
+
+        imgs: [num_images, image_height, image_width, num_channel]
+        returns: masks [num_images, images_height, image_width, 1] with road probabilities
+        """
+        opts = self._options
+        net = self._net
+        world, rank = self._dist.world, self._dist.rank
+
+        num_images = imgs.shape[0]
+        print("Running prediction on {} images... ".format(num_images), end="")
+
+        x = torch.from_numpy(np.ascontiguousarray(imgs, dtype=np.float32)).cuda()
+        if opts.ensemble_prediction:
+            x = images.image_augmentation_ensemble_dev(x)
+            num_images = x.shape[0]
+
+        S, P, B = self.input_size, opts.patch_size, opts.batch_size
+        offset = int((S - P) / 2)
+        x = images.mirror_border_dev(x, offset)
+        H = x.shape[1]
+        assert x.shape[1] == x.shape[2], "Assume square images"
+        assert (H - S) % opts.stride == 0, "Stride sliding should cover the whole image"
+        side = (H - S) // opts.stride + 1
+        num_patches = num_images * side * side
+
+        # this rank's contiguous slice of the patch list
+        k0, k1 = shard_range(num_patches, rank, world)
+        preds = torch.empty(max(k1 - k0, 1), P, P, 1, dtype=torch.float32, device="cuda")
+        batch = self._d_patches
+        for k in range(k0, k1, B):
+            cnt = min(B, k1 - k)
+            # a short tail batch keeps stale patches in the remaining slots (the reference's
+            # intent at :298-301 is zero patches whose outputs are dropped at :315)
+            images.extract_patches_dev(x, S, opts.stride, k, cnt, out=batch)
+            net.forward(batch, keep=1.0)
+            preds[k - k0:k - k0 + cnt, :, :, 0].copy_(net.probs[:cnt])
+
+        # construct masks: overlap average in gather form
+        if world == 1:
+            masks = images.images_from_patches_dev(preds, num_images, side, opts.stride)
+        else:
+            part = images.images_from_patches_dev(preds, num_images, side, opts.stride, k0, k1 - k0,
+                                                  normalize=False)
+            self._dist.dist.all_reduce(part)  # the single exchange of a sharded prediction
+            Sout = part.shape[1]
+            pos = np.arange(Sout)
+            lo = np.where(pos - P + 1 <= 0, 0, (pos - P + opts.stride) // opts.stride)
+            hi = np.minimum(pos // opts.stride, side - 1)
+            cnt1 = (hi - lo + 1).astype(np.float32)
+            cnt2 = torch.from_numpy(np.outer(cnt1, cnt1)).cuda()
+            masks = part / cnt2[None, :, :, None]
+
+        if opts.ensemble_prediction:
+            masks = images.invert_image_augmentation_ensemble_dev(masks[..., 0].contiguous())[..., None]
+
+        print("Prediction Done")
+        return masks.cpu().numpy().astype(np.float64)
+
+    def predict_batchwise(self, imgs, pred_batch_size):
+        masks = []
+        for i in range(int(np.ceil(imgs.shape[0] / pred_batch_size))):
+            start = i * pred_batch_size
+            end = start + pred_batch_size
+            masks.append(self.predict(imgs[start:end]))
+
+        if len(masks) > 1:
+            masks = np.concatenate(masks, axis=0)
+            return masks
+        else:
+            return masks[0]
+
+    # -- checkpoints (tf_aerial_images.py:343-379) -------------------------------------------
+    def save(self, epoch=0):
+        """Writes <save_path>/<experiment_name>/model-epoch-NNN.chkpt (.npz payload + the .meta
+        marker the reference's restore() globs for); all variables incl. momentum slots,
+        global_step and the dead conv_dilut_{L-1} weights, keyed by TensorFlow variable names."""
+        opts = self._options
+        model_data_dir = os.path.abspath(
+            os.path.join(opts.save_path, self.experiment_name, 'model-epoch-{:03d}.chkpt'.format(epoch)))
+        if self._dist.rank == 0:
+            os.makedirs(os.path.dirname(model_data_dir), exist_ok=True)
+            payload = {}
+            for k, v in self._net.state_dict("params").items():
+                payload[k] = v
+            for k, v in self._net.state_dict("momentum").items():
+                payload[k + "/Momentum"] = v
+            payload["global_step"] = np.array(self._net.global_step, dtype=np.int32)
+            with open(model_data_dir, "wb") as f:
+                np.savez(f, **payload)
+            with open(model_data_dir + ".meta", "w") as f:
+                f.write("rsu_b200 checkpoint; num_layers={} root_size={} dilated_layers={}\n".format(
+                    opts.num_layers, opts.root_size, opts.dilated_layers))
+            print("Model saved in file: {}".format(model_data_dir))
+        self._dist.barrier()
+        return model_data_dir
+
+    def restore(self, date=None, epoch=None, file=None):
+        """Restores model from saved checkpoint
+
+        date: which model should be restored (most recent if None)
+        epoch: at which epoch model should be restored (most recent if None)
+        file: provide directly the checkpoint file te restore
+        """
+        opts = self._options
+
+        if file is not None:
+            model_data_dir = file
+        else:
+            # get experiment name to restore from
+            if date is None:
+                dates = [date for date in glob.glob(os.path.join(opts.save_path, "*")) if os.path.isdir(date)]
+                model_data_dir = sorted(dates)[-1]
+            else:
+                model_data_dir = os.path.abspath(os.path.join(opts.save_path, date))
+
+            # get epoch construct final path
+            if epoch is None:
+                model_data_dir = os.path.abspath(os.path.join(model_data_dir, 'model-epoch-*.chkpt.meta'))
+                model_data_dir = sorted(glob.glob(model_data_dir))[-1][:-5]
+            else:
+                model_data_dir = os.path.abspath(
+                    os.path.join(model_data_dir, 'model-epoch-{:03d}.chkpt'.format(epoch)))
+
+        with np.load(model_data_dir) as z:
+            params = {k: z[k] for k in z.files if not k.endswith("/Momentum") and k != "global_step"}
+            mom = {k[:-len("/Momentum")]: z[k] for k in z.files if k.endswith("/Momentum")}
+            step = int(z["global_step"]) if "global_step" in z.files else 0
+        self._net.load_state(params, mom)
+        self._net.global_step = step
+        self._net.pack_weights()
+        print("Model restored from from file: {}".format(model_data_dir))
+
+
+def main(argv=None):
+    flags = make_parser().parse_args(argv)
+    opts = Options(flags)
+    device = '/device:CPU:0' if opts.gpu == -1 else '/device:GPU:{}'.format(opts.gpu)
+    print("Running on device {}".format(device if opts.gpu >= 0 else "cuda:0 (no CPU path exists)"))
+    model = ConvolutionalModel(opts, None)
+
+    if opts.restore_model:
+        if opts.model_path is not None:
+            model.restore(file=opts.model_path)
+            print("Restore model: {}".format(opts.model_path))
+        else:
+            print("Restore date: {}".format(opts.restore_date))
+            model.restore(date=opts.restore_date, epoch=opts.restore_epoch)
+
+    if opts.num_epoch > 0:
+        train_images, train_groundtruth = load_train_data(opts.train_data_dir)
+
+        input_size = unet.input_size_needed(opts.patch_size, opts.num_layers)
+        offset = int((input_size - opts.patch_size) / 2)
+        extended_images = images.expand_and_rotate(train_images, opts.rotation_angles, offset)
+        patches = images.extract_patches(extended_images,
+                                         patch_size=input_size,
+                                         predict_patch_size=opts.patch_size,
+                                         stride=opts.stride)
+
+        print("Train on {} patches of size {}x{}".format(patches.shape[0], patches.shape[1], patches.shape[2]))
+
+        train_groundtruth_exp = images.expand_and_rotate(train_groundtruth, opts.rotation_angles, 0)
+        labels_patches = images.extract_patches(train_groundtruth_exp,
+                                                patch_size=opts.patch_size,
+                                                stride=opts.stride)
+
+        print("Train on {} groundtruth patches of size {}x{}".format(
+            labels_patches.shape[0], labels_patches.shape[1], labels_patches.shape[2]))
+
+        for i in range(opts.num_epoch):
+            print("==== Train epoch: {} ====".format(i))
+            model.train(patches, labels_patches, train_images, train_groundtruth)  # Process one epoch
+            model.save(i)  # Save model to disk
+
+    if opts.eval_data_dir and not opts.eval_train:
+        print("Running inference on eval data {}".format(opts.eval_data_dir))
+        eval_images = load_images(opts.eval_data_dir)
+        start = time.time()
+        masks = model.predict_batchwise(eval_images, opts.pred_batch_size)
+        stop = time.time()
+        print("Prediction time:{} mins".format((stop - start) / 60))
+        masks = images.quantize_mask(masks, patch_size=IMG_PATCH_SIZE, threshold=FOREGROUND_THRESHOLD)
+        np.save(os.path.join(opts.save_path, model.experiment_name + "-masks.npy"), masks)
+    return model
+
+
+def load_images(directory):
+    """PNG directory -> float32 [N,H,W(,C)] in [0,1] (images.load, images.py:24-32) via PIL."""
+    from PIL import Image
+    out = []
+    for file_path in sorted(glob.glob(os.path.join(directory, '*.png'))):
+        out.append(np.asarray(Image.open(file_path), dtype=np.float32) / 255.0)
+    return np.asarray(out)
+
+
+def load_train_data(directory):
+    """images.load_train_data (images.py:240-253)."""
+    return (load_images(os.path.abspath(os.path.join(directory, 'images/'))),
+            load_images(os.path.abspath(os.path.join(directory, 'groundtruth/'))))
+
+
+if __name__ == '__main__':
+    main()

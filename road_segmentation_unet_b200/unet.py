@@ -116,7 +116,12 @@ class UNet:
         self.training = training
         self.seed = seed
         self.global_step = 0
+        # data-parallel hook: called as on_bucket_ready(start, end) when the flat-gradient slice
+        # [start, end) is final, so its all-reduce overlaps the rest of the backward pass
+        self.on_bucket_ready = None
         self._plan_geometry()
+        self._flops = {k: v * batch_size for k, v in
+                       plan_flops(num_layers, root_size, dilated_layers, self.P).items()}
         self._alloc_state(params)
         self._alloc_buffers()
         self.pack_weights()
@@ -169,6 +174,31 @@ class UNet:
         self.momentum = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
         init = params if params is not None else glorot_init(self.L, self.root, self.dilated, self.seed)
         self.load_state(init)
+
+    def _first_offset(self, prefix):
+        for name, off in self.offsets.items():
+            if name.startswith(prefix):
+                return off
+        raise KeyError(prefix)
+
+    def _bucket_bounds(self):
+        """Flat-gradient slices in the order the backward pass completes them: decoder blocks
+        from the last (which also carries the head) to the first, then encoder levels L-1 .. 0
+        (level 0 carries color_space_adjust)."""
+        L = self.L
+        starts = [0]
+        for i in range(1, L):
+            starts.append(self._first_offset("conv_dilut_%d/" % i if self.dilated else "conv_%d/" % i))
+        for j in range(L - 1):
+            starts.append(self._first_offset("up_conv_%d/" % j))
+        ends = starts[1:] + [self.n_flat]
+        enc = list(zip(starts[:L], ends[:L]))
+        dec = list(zip(starts[L:], ends[L:]))
+        return enc, dec
+
+    def _ready(self, bounds):
+        if self.on_bucket_ready is not None:
+            self.on_bucket_ready(bounds[0], bounds[1])
 
     def var(self, name, which="params"):
         flat = getattr(self, which)
@@ -329,11 +359,13 @@ class UNet:
             if i == 0:
                 seed0 = self._site_seed(site)
                 ops.color_im2col(images, w1, b1, 1, 0, 0, self.col, keep, seed0)
+                self._tag(reg1.name)
                 ops.conv_gemm([(self.col, 0, 0)], [(0, 0)], reg1.w_fwd, self.A1[0], f[0],
                               bias=bias(reg1.name), relu=True)
                 if dil_live:
                     d1 = self.convs["conv_dilut_0/atrous_conv1"]
                     ops.color_im2col(images, w1, b1, 2, o2, o2, self.colD, keep, seed0)
+                    self._tag(d1.name)
                     ops.conv_gemm([(self.colD, 0, 0)], [(0, 0)], d1.w_fwd, self.D1[0], f[0],
                                   bias=bias(d1.name), relu=True)
             else:
@@ -344,14 +376,18 @@ class UNet:
                     ops.dropout(src, self._drop_pool[i], keep, self._site_seed(site))
                     src = self._drop_pool[i]
                 net = src
+                self._tag(reg1.name)
                 ops.conv3x3_fwd([(src, 0, 0)], reg1.w_fwd, bias(reg1.name), self.A1[i])
                 if dil_live:
                     d1 = self.convs["conv_dilut_%d/atrous_conv1" % i]
+                    self._tag(d1.name)
                     ops.conv3x3_fwd([(src, o2, o2)], d1.w_fwd, bias(d1.name), self.D1[i], dilation=2)
             site += 1
             if dil_live:
                 d2 = self.convs["conv_dilut_%d/atrous_conv2" % i]
+                self._tag(d2.name)
                 ops.conv3x3_fwd([(self.D1[i], 0, 0)], d2.w_fwd, bias(d2.name), self.D2[i], dilation=2)
+            self._tag(reg2.name)
             ops.conv3x3_fwd([(self.A1[i], 0, 0)], reg2.w_fwd, bias(reg2.name), self.A2[i])
             if i < L - 1:
                 ops.maxpool2x2(self.A2[i], self.Pool[i])
@@ -368,6 +404,7 @@ class UNet:
                 net = self._drop_net[j]
             site += 1
             self._dec_in.append(net)
+            self._tag(up.name)
             ops.upconv2x2_fwd(net, up.w_fwd, bias(up.name), self.U[j])
             t = self.up_size[j]
             so = (self.skip_size[i] - t) // 2
@@ -375,7 +412,9 @@ class UNet:
             if self.dilated:
                 srcs.append((self.D2[i], 0, 0))
             srcs.append((self.U[j], 0, 0))
+            self._tag(c1.name)
             ops.conv3x3_fwd(srcs, c1.w_fwd, bias(c1.name), self.C1[j])
+            self._tag(c2.name)
             ops.conv3x3_fwd([(self.C1[j], 0, 0)], c2.w_fwd, bias(c2.name), self.C2[j])
             net = self.C2[j]
         self._last = net
@@ -394,8 +433,12 @@ class UNet:
         return self.probs
 
     # ------------------------------------------------------------------ backward
+    def _tag(self, name):
+        ops.set_layer(name, self._flops.get(name, 0.0))
+
     def _conv_bwd(self, conv, srcs, dz, dx, mask=None, accumulate=False, need_dx=True):
         """wgrad + bias grad (+ dgrad) of one 3x3 convolution."""
+        self._tag(conv.name)
         g = lambda n: self.var(conv.name + "/" + n, "grads")
         ops.conv3x3_wgrad(srcs, dz, g("kernel").view(-1, conv.cout), dilation=conv.dilation)
         ops.bias_grad(dz, g("bias"))
@@ -405,6 +448,7 @@ class UNet:
 
     def _first_bwd(self, conv, col, dcol, dz, dilation, oy, ox):
         """Cin = 3 convolution through its im2col matrix, plus d(color_space_adjust)."""
+        self._tag(conv.name)
         g = lambda n: self.var(conv.name + "/" + n, "grads")
         conv.dw_stage.zero_()
         ops.wgrad_gemm([(col, 0, 0)], [(0, 0)], dz, (0, 0), conv.dw_stage, (dz.shape[1], dz.shape[2]))
@@ -422,7 +466,7 @@ class UNet:
         L, f = self.L, self.f
         keep = self._keep
         drop = keep < 1.0
-        n_sites = 2 * L - 1
+        enc_buckets, dec_buckets = self._bucket_bounds()
         for j in range(L - 2, -1, -1):
             i = L - 2 - j
             fo = f[i]
@@ -442,6 +486,7 @@ class UNet:
             d_up = dcat[..., (2 if self.dilated else 1) * fo:]
             x_in = self._dec_in[j]
             g = lambda n: self.var(up.name + "/" + n, "grads")
+            self._tag(up.name)
             ops.upconv2x2_wgrad(d_up, x_in, g("kernel").view(4 * up.cout, up.cin))
             ops.bias_grad(d_up, g("bias"))
             # gradient into the tensor that fed the transpose conv (previous decoder output, or
@@ -453,6 +498,7 @@ class UNet:
             ops.upconv2x2_dgrad(d_up, up.w_dgrad, dst, mask=x_in if drop else act)
             if drop:
                 ops.dropout(dst, dst, keep, self._site_seed(L + j))
+            self._ready(dec_buckets[j])
         for i in range(L - 1, -1, -1):
             reg1, reg2 = self.convs["conv_%d/conv1" % i], self.convs["conv_%d/conv2" % i]
             dil_live = self.dilated and i < L - 1
@@ -482,6 +528,7 @@ class UNet:
                     self._conv_bwd(d1, [(src, o2, o2)], self.dD1[i], win, accumulate=True)
                 else:
                     self._first_bwd(d1, self.colD, self.dcolD, self.dD1[0], 2, o2, o2)
+            self._ready(enc_buckets[i])
 
     # ------------------------------------------------------------------ optimizer
     def learning_rate(self, lr0):
@@ -530,3 +577,43 @@ def forward(X, num_layers, root_size, dilated_layers, dropout_keep=None, params=
     keep = 1.0 if dropout_keep is None else float(dropout_keep)
     net.forward(x, keep=keep, want_logits=True)
     return net.logits.cpu().numpy()
+
+
+def plan_flops(num_layers, root_size, dilated_layers, patch_size):
+    """Algorithmic forward FLOPs per patch of every live layer (SURVEY.md 8(d) "F_min"):
+    2 * k^2 * Cin * Cout * Hout^2 per convolution with Hout the extent actually consumed
+    downstream (dilated branches only on the window the decoder crops), 2 * 4 * Cin * Cout * Hin^2
+    per transpose convolution; dead layers count zero.  Returns an OrderedDict name -> FLOPs."""
+    L, f0 = num_layers, root_size
+    S = input_size_needed(patch_size, L)
+    f = [f0 * 2 ** i for i in range(L)]
+    in_size, s = [], S
+    for i in range(L):
+        in_size.append(s)
+        s = (s - 4) // 2
+    skip = [v - 4 for v in in_size]
+    up, net = [], skip[L - 1]
+    for j in range(L - 1):
+        up.append(2 * net)
+        net = 2 * net - 4
+    out = OrderedDict()
+    out["color_space_adjust"] = 2 * 3 * 3 * S * S
+    for i in range(L):
+        cin = 3 if i == 0 else f[i - 1]
+        if dilated_layers and i < L - 1:
+            t = up[L - 2 - i]
+            out["conv_dilut_%d/atrous_conv1" % i] = 2 * 9 * cin * f[i] * (t + 4) ** 2
+            out["conv_dilut_%d/atrous_conv2" % i] = 2 * 9 * f[i] * f[i] * t ** 2
+        out["conv_%d/conv1" % i] = 2 * 9 * cin * f[i] * (in_size[i] - 2) ** 2
+        out["conv_%d/conv2" % i] = 2 * 9 * f[i] * f[i] * (in_size[i] - 4) ** 2
+    net_c, net = f[L - 1], skip[L - 1]
+    for j in range(L - 1):
+        fo = f[L - 2 - j]
+        out["up_conv_%d" % j] = 2 * 4 * net_c * fo * net ** 2
+        t = 2 * net
+        cat = fo * (3 if dilated_layers else 2)
+        out["conv_%d/conv1" % (L + j)] = 2 * 9 * cat * fo * (t - 2) ** 2
+        out["conv_%d/conv2" % (L + j)] = 2 * 9 * fo * fo * (t - 4) ** 2
+        net_c, net = fo, t - 4
+    out["weight_output"] = 2 * net_c * 2 * net ** 2
+    return out

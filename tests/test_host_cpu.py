@@ -1,0 +1,146 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every symbol the header
+declares, the flag surface matches the reference, FLOP accounting matches SURVEY.md, and the
+data-parallel plumbing (gradient buckets + rank sharding) works at world_size 2 over gloo."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    from road_segmentation_unet_b200 import _lib
+    lib = _lib.load()  # no compute calls: loading must work without a GPU
+    header = open(os.path.join(ROOT, "include", "rsu_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|void|long long|const char\*)\s+(rsu_[a-z0-9_]+)\s*\(", header, re.M))
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), "librsu_b200.so does not export %s" % name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.rsu_version() >= 100
+    assert lib.rsu_last_error() is not None
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from road_segmentation_unet_b200 import unet
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        unet.UNet(3, 64, False, 1, 60)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "road_segmentation_unet_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", ""), name
+
+
+def test_flags_match_reference_defaults():
+    """tf_aerial_images.py:15-46 -- names and defaults verbatim."""
+    from road_segmentation_unet_b200 import tf_aerial_images as tfa
+    o = tfa.Options()
+    expect = dict(batch_size=25, dilated_layers=False, dropout=0.8, ensemble_prediction=False,
+                  eval_data_dir=None, eval_every=500, eval_train=False, gpu=-1, image_augmentation=False,
+                  interactive=False, lr=0.01, model_path=None, momentum=0.9, num_epoch=5,
+                  num_eval_images=4, num_gpu=1, num_layers=5, patch_size=128, pred_batch_size=2,
+                  restore_date=None, restore_epoch=None, restore_model=False, root_size=64,
+                  rotation_angles=None, seed=2017, stride=16, train_score_every=1000)
+    for k, v in expect.items():
+        assert getattr(o, k) == v, k
+    assert len(tfa.FLAG_DEFS) == 30
+    f = tfa.make_parser().parse_args(["--rotation_angles", "15,30", "--dilated_layers", "--num_layers", "6"])
+    o = tfa.Options(f)
+    assert o.rotation_angles == [15, 30] and o.dilated_layers is True and o.num_layers == 6
+
+
+def test_constants():
+    from road_segmentation_unet_b200 import constants as c
+    assert (c.FOREGROUND_THRESHOLD, c.IMG_PATCH_SIZE, c.NUM_CHANNELS, c.NUM_LABELS, c.PIXEL_DEPTH) == \
+        (.25, 16, 3, 2, 255)
+
+
+def test_input_size_and_flops():
+    from road_segmentation_unet_b200 import unet
+    assert [unet.input_size_needed(388, L) for L in (4, 5, 6)] == [476, 572, 764]
+    with pytest.raises(AssertionError):
+        unet.input_size_needed(390, 4)
+    fl = unet.plan_flops(6, 64, True, 388)
+    assert abs(sum(fl.values()) / 1e9 - 680.82) < 0.01          # F_min, SURVEY.md 8(d)
+    assert "conv_dilut_5/atrous_conv1" not in fl                   # dead pair counts zero
+    assert abs(sum(unet.plan_flops(4, 64, False, 388).values()) / 1e9 - 195.59) < 0.01
+    shapes = unet.variable_shapes(6, 64, True)
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 212403278
+    a = unet.glorot_init(3, 64, True, 2017)
+    b = unet.glorot_init(3, 64, True, 2017)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_host_scoring_rules():
+    """quantize_mask / labels_for_patches keep the reference rules (images.py:88-99, 256-266)."""
+    from road_segmentation_unet_b200 import images
+    from oracle import images_oracle as IO
+    G = np.load(os.path.join(ROOT, "tests", "golden", "images_golden.npz"))
+    assert np.array_equal(images.quantize_mask(G["quant_in"], 0.25, 16), G["quant_out"])
+    p = np.zeros((3, 4, 4))
+    p[1] = 1.0
+    p[2, :1] = 1.0  # mean 0.25 is NOT > 0.25
+    assert images.labels_for_patches(p).tolist() == [0, 1, 0]
+    assert images.predictions_to_patches(np.array([0, 1]), 2).shape == (2, 2, 2, 1)
+    assert IO.patch_f1(G["quant_in"], G["quant_in"]) == 1.0
+
+
+def test_shard_helpers():
+    from road_segmentation_unet_b200 import tf_aerial_images as tfa
+    for n in (1, 7, 2166, 17328):
+        for world in (1, 2, 4, 8):
+            cover = []
+            for r in range(world):
+                k0, k1 = tfa.shard_range(n, r, world)
+                cover.extend(range(k0, k1))
+            assert cover == list(range(n))
+    idx = np.arange(100)
+    got = [tfa.rank_batch_indices(idx, 32, r, 8).tolist() for r in range(4)]
+    assert sum(got, []) == list(range(32, 64))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, bounds, n_flat, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from road_segmentation_unet_b200 import tf_aerial_images as tfa
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(n_flat, dtype=torch.float32) * (rank + 1)
+    red = tfa.GradientAllReducer(dist, world, g)
+    for (a, b) in bounds:  # buckets become ready in backward order
+        red.bucket_ready(a, b)
+    scale = red.finish()
+    np.save(os.path.join(out_dir, "g%d.npy" % rank), (g * scale).numpy())
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_buckets_gloo(tmp_path):
+    """world_size 2 on CPU: bucketed all-reduce == mean over ranks, every element exactly once."""
+    import torch.multiprocessing as mp
+    n_flat = 1000
+    bounds = [(700, 1000), (300, 700), (0, 300)]
+    port = _free_port()
+    mp.spawn(_dp_worker, args=(2, port, bounds, n_flat, str(tmp_path)), nprocs=2, join=True)
+    expect = np.arange(n_flat, dtype=np.float32) * 1.5  # mean of x*1 and x*2
+    for r in range(2):
+        assert np.allclose(np.load(str(tmp_path / ("g%d.npy" % r))), expect)

@@ -1,0 +1,148 @@
+"""Geometry kernels (csrc/geometry.cu through road_segmentation_unet_b200.images) against the
+golden vectors produced by the reference's own src/images.py and against the NumPy oracle.
+Bit-exact for padding, flips, 90-degree rotations, crops and patch indexing (BASELINE.json
+north_star); <= 1e-6 for the two averaging helpers (fp64 accumulation on the device)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import images_oracle as IO
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "images_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def images():
+    from road_segmentation_unet_b200 import images as _images
+    return _images
+
+
+def test_mirror_border(images):
+    out = images.mirror_border(G["mirror_in4"], 4)
+    assert out.dtype == G["mirror_out4_n4"].dtype and np.array_equal(out, G["mirror_out4_n4"])
+    assert np.array_equal(images.mirror_border(G["mirror_in3"], 7), G["mirror_out3_n7"])
+    rs = np.random.RandomState(0)
+    x64 = rs.rand(2, 33, 33, 3)  # float64 moves bit-exactly as word pairs
+    assert np.array_equal(images.mirror_border(x64, 20), IO.mirror_border(x64, 20))
+    # full-size: 6 x 604^2 x 3 -> 980^2 (config 3), pad larger than nothing special
+    x = rs.rand(6, 604, 604, 3).astype(np.float32)
+    assert np.array_equal(images.mirror_border(x, 188), np.pad(x, ((0, 0), (188, 188), (188, 188), (0, 0)), "symmetric"))
+    # pad larger than the image (periodic reflection)
+    small = rs.rand(1, 5, 5, 1).astype(np.float32)
+    assert np.array_equal(images.mirror_border(small, 12), np.pad(small, ((0, 0), (12, 12), (12, 12), (0, 0)), "symmetric"))
+
+
+def test_extract_patches(images):
+    x = G["extract_in"]
+    for got, ref in ((images.extract_patches(x, 8, stride=4), G["extract_p8_s4"]),
+                     (images.extract_patches(x, 10), G["extract_p10_nostride"]),
+                     (images.extract_patches(x[..., 0], 12, stride=8), G["extract3d_p12_s8"])):
+        assert got.dtype == np.float64 and got.shape == ref.shape and np.array_equal(got, ref)
+    with pytest.raises(AssertionError):
+        images.extract_patches(x, 8, stride=5)
+    with pytest.raises(AssertionError):
+        images.extract_patches(np.zeros((1, 8, 9, 3), np.float32), 4)
+    # the reference's own shape tests (src/test_images.py:11-45)
+    imgs = np.random.RandomState(1).rand(2, 608, 608, 3).astype(np.float32)
+    p = images.extract_patches(imgs, 128, 16)
+    assert p.shape == (2 * 31 * 31, 128, 128, 3)
+    # x-outer ordering: patch k of image n sits at (x = k // side * stride, y = k % side * stride)
+    k = 31 * 5 + 7
+    assert np.array_equal(p[k], imgs[0, 7 * 16:7 * 16 + 128, 5 * 16:5 * 16 + 128])
+    assert np.array_equal(p[961 + k], imgs[1, 7 * 16:7 * 16 + 128, 5 * 16:5 * 16 + 128])
+    # device-level range extraction = a slice of the full list
+    xd = torch.tensor(imgs).cuda()
+    part = images.extract_patches_dev(xd, 128, 16, k_begin=950, k_count=40).cpu().numpy()
+    assert np.array_equal(part, p[950:990].astype(np.float32))
+
+
+def test_images_from_patches(images):
+    for key_in, stride, key_out in (("from_patches_in", 4, "from_patches_s4"),
+                                    ("from_patches_in", None, "from_patches_nostride"),
+                                    ("from_patches_in64", 3, "from_patches64_s3")):
+        got = images.images_from_patches(G[key_in], stride=stride)
+        assert got.shape == G[key_out].shape
+        assert np.abs(got - G[key_out]).max() <= 1e-6
+    # round trip with extract_patches is exact
+    x = np.random.RandomState(2).rand(2, 44, 44, 1).astype(np.float32)
+    pt = images.extract_patches(x, 20, stride=12).reshape(2, 9, 20, 20, 1)
+    assert np.abs(images.images_from_patches(pt, stride=12) - x).max() == 0.0
+    # config-3 geometry at reduced patch count: P=388, stride 12, side 5
+    pr = np.random.RandomState(3).rand(1, 25, 388, 388, 1).astype(np.float32)
+    got = images.images_from_patches(pr, stride=12)
+    ref = IO.images_from_patches(pr.astype(np.float64), stride=12)
+    assert got.shape == (1, 436, 436, 1) and np.abs(got - ref).max() <= 1e-6
+    # sharded form: partial sums of two slices add up to the normalised result
+    pd = torch.tensor(pr.reshape(25, 388, 388, 1)).cuda()
+    a = images.images_from_patches_dev(pd[:11], 1, 5, 12, 0, 11, normalize=False)
+    b = images.images_from_patches_dev(pd[11:], 1, 5, 12, 11, 14, normalize=False)
+    hits = IO.images_from_patches(np.ones_like(pr, dtype=np.float64) * 0 + 1, stride=12)  # all ones
+    cnt = np.zeros((436, 436))
+    for kx in range(5):
+        for ky in range(5):
+            cnt[ky * 12:ky * 12 + 388, kx * 12:kx * 12 + 388] += 1
+    assert np.abs((a + b).cpu().numpy()[0, :, :, 0] / cnt - ref[0, :, :, 0]).max() <= 1e-6
+    assert hits.shape == ref.shape
+
+
+def test_ensemble(images):
+    got = images.image_augmentation_ensemble(G["ens_in"])
+    assert got.dtype == np.float64 and np.array_equal(got, G["ens_out"])
+    inv = images.invert_image_augmentation_ensemble(G["inv_in"])
+    assert np.abs(inv - G["inv_out"]).max() <= 1e-6
+    x = np.random.RandomState(4).rand(2, 604, 604, 3).astype(np.float32)
+    assert np.array_equal(images.image_augmentation_ensemble(x), IO.image_augmentation_ensemble(x))
+    m = np.random.RandomState(5).rand(2, 37, 37, 1).astype(np.float32)
+    rt = images.invert_image_augmentation_ensemble(images.image_augmentation_ensemble(m))
+    assert np.abs(rt - m).max() <= 1e-6
+
+
+@pytest.mark.parametrize("dtype,shape", [(torch.float32, (9, 50, 50, 3)), (torch.uint8, (8, 37, 37)),
+                                          (torch.float32, (8, 764, 764, 3))])
+def test_d4_transform(images, dtype, shape):
+    """All 8 dihedral elements, bit-exact: out = rot90(flipud(x) if op & 4 else x, k = op & 3)
+    (tf.image.flip_up_down / rot90 of tf_aerial_images.py:173-210, np.flip / np.rot90 of
+    images.py:376-417)."""
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(shape, generator=g) * 255).to(dtype)
+    ops_np = (np.arange(shape[0]) % 8).astype(np.uint8)
+    out = images.d4_transform_dev(x.cuda(), torch.tensor(ops_np).cuda()).cpu().numpy()
+    for i, op in enumerate(ops_np):
+        assert np.array_equal(out[i], IO.d4(x[i].numpy(), int(op))), (i, op)
+
+
+def test_crop(images):
+    assert np.array_equal(images.crop_imgs(G["crop_in"], 8), G["crop_out8"])
+    with pytest.raises(AssertionError):
+        images.crop_imgs(G["crop_in"], 7)
+
+
+@pytest.mark.parametrize("angle", [15, 30, 45, 60, 75, 90])
+def test_rotate(images, angle):
+    """Nearest-neighbour rotation against SciPy (golden) -- exact on the golden input; on a larger
+    random image half-integer ties at 30/60 degrees may resolve differently."""
+    got = images.rotate_imgs(G["rot_in"], angle)
+    ref = G["rot_%d" % angle]
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    assert np.array_equal(got, ref)
+    x = np.random.RandomState(6).rand(1, 200, 200, 3).astype(np.float32)
+    big = images.rotate_imgs(x, angle)
+    ref_big = IO.rotate_nn(x, angle)
+    assert big.shape == ref_big.shape
+    mismatch = float((big != ref_big).any(axis=-1).mean())
+    assert mismatch <= (1e-3 if angle in (30, 60) else 0.0), mismatch
+
+
+def test_expand_and_rotate(images):
+    got = images.expand_and_rotate(G["expand_in"], [0, 15, 45, 75], 6)
+    assert got.dtype == np.float64 and np.array_equal(got, G["expand_off6"])
+    assert np.array_equal(images.expand_and_rotate(G["expand_in"][..., 0], [30, 60], 0), G["expand3d_off0"])
+    # training-prep geometry of the README config on one synthetic 400^2 image (offset 188)
+    x = np.random.RandomState(7).rand(1, 400, 400, 3).astype(np.float32)
+    got = images.expand_and_rotate(x, [15, 45, 75], 188)
+    ref = IO.expand_and_rotate(x, [15, 45, 75], 188)
+    assert got.shape == (3, 776, 776, 3)
+    assert float((got != ref).any(axis=-1).mean()) == 0.0

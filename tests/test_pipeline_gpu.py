@@ -1,0 +1,140 @@
+"""ConvolutionalModel (train / predict / save / restore) on the GPU against the oracle pipeline.
+
+End-to-end gate of BASELINE.json: predicted road masks in >= 99.5 % pixel agreement with the
+reference path and patch-level F1 within 0.002, on identical weights and synthetic inputs.  The
+weights come from a short training run of the engine itself on a learnable synthetic task (blob
+masks), so that probabilities are confident like a real model's rather than ~0.5 everywhere.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import images_oracle as IO
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def blobs(rs, n, size, cells=6):
+    low = rs.rand(n, 1, cells, cells).astype(np.float32)
+    up = F.interpolate(torch.tensor(low), size=(size, size), mode="bilinear", align_corners=False)
+    return (up.numpy()[:, 0] > 0.55).astype(np.float32)
+
+
+def make_data(rs, n, size):
+    lab = blobs(rs, n, size)
+    img = np.stack([0.25 + 0.5 * lab + 0.1 * rs.randn(n, size, size) for _ in range(3)], -1)
+    img[..., 1] = 0.5 + 0.1 * rs.randn(n, size, size)
+    return np.clip(img, 0, 1).astype(np.float32), lab
+
+
+def make_model(tmp_path, **kw):
+    from road_segmentation_unet_b200 import tf_aerial_images as tfa
+    opts = tfa.Options()
+    opts.num_layers, opts.root_size, opts.dilated_layers = 3, 64, True
+    opts.patch_size, opts.batch_size, opts.stride = 36, 4, 12
+    opts.dropout, opts.lr, opts.momentum = 1.0, 0.02, 0.9
+    opts.ensemble_prediction = True
+    opts.save_path = str(tmp_path)
+    opts.eval_every = opts.train_score_every = 10 ** 9
+    for k, v in kw.items():
+        setattr(opts, k, v)
+    return tfa.ConvolutionalModel(opts, None), opts
+
+
+def oracle_predict(imgs, params, opts, S):
+    """The reference's predict() (tf_aerial_images.py:271-328) restated with the CPU oracle."""
+    x = IO.image_augmentation_ensemble(imgs) if opts.ensemble_prediction else imgs
+    n_img = x.shape[0]
+    off = (S - opts.patch_size) // 2
+    patches = IO.extract_patches(IO.mirror_border(x, off), S, stride=opts.stride,
+                                 predict_patch_size=opts.patch_size)
+    tp = O.to_torch(params)
+    preds = []
+    with torch.no_grad():
+        for k in range(0, patches.shape[0], 16):
+            logits = O.forward(torch.tensor(patches[k:k + 16], dtype=torch.float32), tp,
+                               opts.num_layers, opts.root_size, opts.dilated_layers)
+            preds.append(torch.softmax(logits, dim=3)[..., 1].numpy())
+    preds = np.concatenate(preds).astype(np.float64)
+    per_img = patches.shape[0] // n_img
+    masks = IO.images_from_patches(preds.reshape(n_img, per_img, opts.patch_size, opts.patch_size, 1),
+                                   stride=opts.stride)
+    if opts.ensemble_prediction:
+        masks = IO.invert_image_augmentation_ensemble(masks)
+    return masks
+
+
+def test_train_then_predict_parity(tmp_path):
+    model, opts = make_model(tmp_path)
+    S = model.input_size
+    assert S == 76
+    off = (S - opts.patch_size) // 2
+    rs = np.random.RandomState(0)
+    losses = []
+    for step in range(30):
+        img, lab = make_data(rs, opts.batch_size, S)
+        loss, probs = model.train_batch(img, lab[:, off:off + 36, off:off + 36])
+        losses.append(loss)
+        assert probs.shape == (4, 36, 36)
+    assert model.global_step == 30
+    assert np.mean(losses[-5:]) < 0.35 < losses[0], losses  # the engine learns the task
+
+    params = model.net.state_dict()
+    imgs, labels = make_data(np.random.RandomState(1), 2, 84)  # (84 + 40 - 76) % 12 == 0 -> 5x5 patches
+    masks = model.predict(imgs)
+    assert masks.shape == (2, 84, 84, 1) and masks.dtype == np.float64
+    ref = oracle_predict(imgs, params, opts, S)
+    assert ref.shape == masks.shape
+    agree = float(((masks > 0.5) == (ref > 0.5)).mean())
+    f1_dev, f1_ref = IO.patch_f1(masks, labels[..., None]), IO.patch_f1(ref, labels[..., None])
+    print("pixel agreement %.5f  max|dp| %.4f  F1 device %.4f  oracle %.4f"
+          % (agree, np.abs(masks - ref).max(), f1_dev, f1_ref))
+    assert agree >= 0.995
+    assert abs(f1_dev - f1_ref) <= 0.002
+    assert f1_ref > 0.5  # the synthetic task was actually learnt
+    assert np.abs(masks - ref).mean() < 5e-3
+
+    # without the ensemble and through predict_batchwise
+    opts.ensemble_prediction = False
+    m2 = model.predict_batchwise(imgs, 1)
+    r2 = oracle_predict(imgs, params, opts, S)
+    assert m2.shape == (2, 84, 84, 1)
+    assert float(((m2 > 0.5) == (r2 > 0.5)).mean()) >= 0.995
+
+    # checkpoint round trip: reference file naming, momentum slots and global_step included
+    path = model.save(3)
+    assert path.endswith("model-epoch-003.chkpt")
+    model2, _ = make_model(tmp_path, ensemble_prediction=False)
+    model2.restore(file=path)
+    assert model2.global_step == 30
+    assert np.array_equal(model2.predict(imgs), m2)
+    for k, v in model.net.state_dict("momentum").items():
+        assert np.array_equal(model2.net.state_dict("momentum")[k], v), k
+    model3, _ = make_model(tmp_path, ensemble_prediction=False)
+    model3.experiment_name = "zzz-other"
+    model3.restore()  # latest directory / latest epoch resolution (tf_aerial_images.py:351-379)
+    assert np.array_equal(model3.predict(imgs), m2)
+
+
+def test_train_epoch_semantics(tmp_path):
+    """train(): labels binarised at 0.5, shuffled indices, range(0, n - B, B) drops the last batch
+    even when n is divisible (tf_aerial_images.py:221-232); augmentation keeps images and masks
+    aligned (both transformed by the same dihedral element)."""
+    model, opts = make_model(tmp_path, image_augmentation=True, dropout=0.8)
+    S = model.input_size
+    off = (S - 36) // 2
+    rs = np.random.RandomState(2)
+    img, lab = make_data(rs, 12, S)
+    model.train(img.astype(np.float64), lab[:, off:off + 36, off:off + 36] * 0.9, img, lab)
+    assert model.global_step == len(range(0, 12 - 4, 4)) == 2
+    assert len(model.scalars) == 2 and all(np.isfinite(s[1]) for s in model.scalars)
+    x = torch.tensor(img[:4]).cuda()
+    y = torch.tensor((lab[:4, off:off + 36, off:off + 36] > 0.5).astype(np.uint8)).cuda()
+    xa, ya = model.stochastic_images_augmentation(x, y)
+    # recover the op from the image, then the mask must have moved identically
+    for i in range(4):
+        ops_i = [op for op in range(8) if np.array_equal(IO.d4(x[i].cpu().numpy(), op), xa[i].cpu().numpy())]
+        assert len(ops_i) == 1
+        assert np.array_equal(IO.d4(y[i].cpu().numpy(), ops_i[0]), ya[i].cpu().numpy())

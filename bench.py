@@ -236,6 +236,16 @@ def run_gpu(args):
     ms_per_step = ms / K
     value = world * B * K / (ms / 1e3)
 
+    if args.quick:  # profiling runs (ncu): only the device-timed region
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+                              "warmup": W, "ms_per_step": ms_per_step, "gpu_launches": launches,
+                              "quick": True}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the public API: pinned host batch in, loss + probabilities out
     xp = torch.from_numpy(xh).pin_memory()
     lp = torch.from_numpy(lh).pin_memory()
@@ -267,6 +277,16 @@ def run_gpu(args):
         for _ in range(kp):
             device_step()
         rec = ops.profile_stop()
+        if args.dump_layers:
+            per = {}
+            for kind, layer, fl, t_ms in rec:
+                a = per.setdefault("%s|%s" % (kind, layer), [0.0, 0.0, 0])
+                a[0] += fl / kp
+                a[1] += t_ms / kp
+                a[2] += 1
+            with open(args.dump_layers, "w") as f:
+                json.dump({k: {"alg_gflop": v[0] / 1e9, "ms": v[1], "launches": v[2] / kp,
+                               "tflops": v[0] / max(v[1], 1e-9) / 1e9} for k, v in per.items()}, f, indent=1)
         by_kind = {}
         for kind, layer, fl, t_ms in rec:
             a = by_kind.setdefault(kind, [0.0, 0.0, 0])
@@ -336,6 +356,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 32 = the named config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--quick", action="store_true", help="device-timed region only (for ncu runs)")
+    ap.add_argument("--dump-layers", default="", help="write the per-layer tcgen05 kernel timing table here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -71,6 +71,7 @@ typedef struct {
   const void* mask; /* bf16, same indexing as out with its own strides: keep where mask > 0 */
   long long mask_sn, mask_sy, mask_sx;
   int accumulate; /* out += result */
+  int algo;       /* 0 = choose, 1 = one TMA box per tap, 2 = halo tile shared by all taps */
 } rsu_conv_gemm_desc;
 int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream);
 
@@ -87,6 +88,11 @@ typedef struct {
   int H, W, N_img; /* pixel grid that is summed over */
   float* out;
   int ldo; /* row stride of out (>= grad.C) */
+  float* bias_grad; /* optional fp32 [Cout]: += column sums of grad over the pixel grid
+                       (BiasAddGrad fused into the halo-tile kernel; NULL = not wanted).  On
+                       return *bias_done tells whether the kernel produced it. */
+  int* bias_done_host;
+  int algo; /* 0 = choose, 1 = one TMA box per tap pair, 2 = halo tile shared by all taps */
 } rsu_wgrad_desc;
 int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream);
 

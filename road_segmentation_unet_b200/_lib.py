@@ -28,14 +28,15 @@ class ConvGemmDesc(C.Structure):
                 ("out_sn", C.c_longlong), ("out_sy", C.c_longlong), ("out_sx", C.c_longlong),
                 ("shuffle_cout", C.c_int), ("bias", C.c_void_p), ("relu", C.c_int),
                 ("mask", C.c_void_p), ("mask_sn", C.c_longlong), ("mask_sy", C.c_longlong),
-                ("mask_sx", C.c_longlong), ("accumulate", C.c_int)]
+                ("mask_sx", C.c_longlong), ("accumulate", C.c_int), ("algo", C.c_int)]
 
 
 class WgradDesc(C.Structure):
     _fields_ = [("n_src", C.c_int), ("src", View * RSU_MAX_SRC), ("n_taps", C.c_int),
                 ("tap_dy", C.c_int * RSU_MAX_TAPS), ("tap_dx", C.c_int * RSU_MAX_TAPS),
                 ("grad", View), ("H", C.c_int), ("W", C.c_int), ("N_img", C.c_int),
-                ("out", C.c_void_p), ("ldo", C.c_int)]
+                ("out", C.c_void_p), ("ldo", C.c_int), ("bias_grad", C.c_void_p),
+                ("bias_done_host", C.POINTER(C.c_int)), ("algo", C.c_int)]
 
 
 class RsuError(RuntimeError):

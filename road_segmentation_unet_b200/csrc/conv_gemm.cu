@@ -44,11 +44,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
   const uint32_t bias_base = tmem_slot + 16u;  // float [2][256]
+  const uint32_t ktab_base = bias_base + 2u * 256u * 4u;  // int4 [num_k]
   // generic pointers to the same carve-up
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   float* bias_s = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
+  int4* ktab = reinterpret_cast<int4*>(smem_gen + (ktab_base - smem_base));
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&p.a_map[s]);
@@ -77,11 +79,22 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   for (int s = 0; s < p.n_src; ++s) chunks_total += p.src_chunks[s];
   const int num_k = p.n_taps * chunks_total;
   const uint32_t a_bytes = static_cast<uint32_t>(p.TW * p.TH) * 128u;
+  // K-step table (tile independent): {source index, first channel, x offset, y offset}.  The
+  // single-warp producer loop is issue-latency bound, so everything that does not depend on the
+  // tile is looked up with one 16-byte shared-memory load instead of being recomputed.
+  for (int k = threadIdx.x; k < num_k; k += kConvThreads) {
+    const int t = k / chunks_total;
+    int cg = k % chunks_total, s = 0;
+    while (s < p.n_src - 1 && cg >= p.src_chunks[s]) cg -= p.src_chunks[s++];
+    ktab[k] = make_int4(s, cg * kBlockK, p.tap_dx[t] + p.src_off_x[s], p.tap_dy[t] + p.src_off_y[s]);
+  }
+  __syncthreads();
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
+    // (whole warp converged, one elected lane issues: keeps the loop on the uniform datapath)
+    uint32_t stage = 0, phase = 0;
+    const uint32_t tx_bytes = a_bytes + b_stage_bytes;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles_n;
       const int rest = tile / p.n_tiles_n;
@@ -89,30 +102,27 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const int ty = (rest / p.tiles_x) % p.tiles_y;
       const int img = rest / tiles_per_img;
       const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = n_tile * p.BN;
-      int kk = 0;
-      for (int t = 0; t < p.n_taps; ++t) {
-        for (int s = 0; s < p.n_src; ++s) {
-          const int cx = x0 + p.tap_dx[t] + p.src_off_x[s];
-          const int cy = y0 + p.tap_dy[t] + p.src_off_y[s];
-          for (int c = 0; c < p.src_chunks[s]; ++c, ++kk) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * stage_bytes;
-            mbar_expect_tx(full_bar(stage), a_bytes + b_stage_bytes);
-            tma_load_4d(a_dst, &p.a_map[s], full_bar(stage), c * kBlockK, cx, cy, img);
-            tma_load_2d(a_dst + kAStageBytes, &p.b_map, full_bar(stage), kk * kBlockK, n0);
-            if (++stage == stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
+      for (int k = 0; k < num_k; ++k) {
+        const int4 e = ktab[k];
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t a_dst = smem_base + stage * stage_bytes;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, tx_bytes);
+          tma_load_4d(a_dst, &p.a_map[e.x], fb, e.y, x0 + e.z, y0 + e.w, img);
+          tma_load_2d(a_dst + kAStageBytes, &p.b_map, fb, k * kBlockK, n0);
+        }
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(stages)) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, false, false);
-    int stage = 0;
-    uint32_t phase = 0;
+    uint32_t stage = 0, phase = 0;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
       const uint32_t acc = acc_it & 1u;
@@ -123,21 +133,25 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       for (int k = 0; k < num_k; ++k) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * stage_bytes;
-        const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(a_addr + kAStageBytes, 16, 1024);
+        if (elect_one()) {
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(a_addr + kAStageBytes, 16, 1024);
 #pragma unroll
-        for (int j = 0; j < kBlockK / 16; ++j) {
-          // advancing 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in >>4 units
-          umma_bf16(d_tmem, adesc + 2u * j, bdesc + 2u * j, idesc, (k | j) != 0 ? 1u : 0u);
+          for (int j = 0; j < kBlockK / 16; ++j) {
+            // advancing 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in >>4 units
+            umma_bf16(d_tmem, adesc + 2u * j, bdesc + 2u * j, idesc, (k | j) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
         }
-        umma_commit(empty_bar(stage));
-        if (++stage == stages) {
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(stages)) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(tfull_bar(acc));
+      if (elect_one()) umma_commit(tfull_bar(acc));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
@@ -246,14 +260,17 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 }
 
 // ------------------------------------------------------------------ host launcher
-static int conv_smem_bytes(int BN, int* stages_out) {
+static int conv_smem_bytes(int BN, int num_k, int* stages_out) {
   const int stage_bytes = kAStageBytes + BN * 128;
-  int stages = (200 * 1024) / stage_bytes;
+  const int fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 4) + 16 + 2 * 256 * 4 + 16 * num_k /*k-step table*/;
+  int stages = (226 * 1024 - fixed) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   *stages_out = stages;
-  return 1024 /*align slack*/ + stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 2 * 256 * 4;
+  return fixed + stages * stage_bytes;
 }
+
+int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forced);  // conv_halo.cu
 
 }  // namespace rsu
 
@@ -276,6 +293,19 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
   if (d->shuffle_cout > 0 && (d->Ntot != 4 * d->shuffle_cout || d->shuffle_cout % 32 != 0))
     return set_error(RSU_EINVAL, "shuffle_cout %d inconsistent with Ntot %d", d->shuffle_cout,
                      d->Ntot);
+
+  // Halo-tile kernel for the layers whose per-tap operand traffic (L2 -> SM) bounds them: few
+  // output channels per tile and a large pixel grid.
+  // (thresholds from the per-layer A/B table, profiles/r1_layers_ab.md)
+  const bool want_halo =
+      d->algo == 2 ||
+      (d->algo == 0 && d->n_taps == 9 && d->H_out >= 64 && d->W_out >= 64 &&
+       (d->Ntot <= 192 || (d->Ntot <= 384 && d->Ntot % 128 == 0 && d->H_out >= 190)));
+  if (want_halo) {
+    const int rc = launch_conv_halo(d, stream, d->algo == 2);
+    if (rc >= 0) return rc;
+    if (d->algo == 2) return set_error(RSU_EINVAL, "shape not eligible for the halo-tile kernel");
+  }
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -332,7 +362,8 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
   p.accumulate = d->accumulate;
 
   int stages;
-  const int smem = conv_smem_bytes(p.BN, &stages);
+  const int smem = conv_smem_bytes(p.BN, ktot / kBlockK, &stages);
+  if (smem > 227 * 1024) return set_error(RSU_EINVAL, "K = %d too deep for the k-step table", ktot);
   static bool attr_set = false;
   if (!attr_set) {
     RSU_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel,

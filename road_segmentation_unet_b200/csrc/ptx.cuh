@@ -13,6 +13,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One elected lane of a converged warp (the same lane every time for the full mask).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -41,6 +52,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05 operands)
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- TMA
@@ -92,6 +108,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the two 64-bit descriptors given as (lo, hi) halves: only the lo word (start
+// address, LBO) changes between the instructions of a tile, so callers keep hi constant and
+// advance lo with one 32-bit add.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                               uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// hi word of a SWIZZLE_128B descriptor: stride byte offset, version 1, layout type 2
+__device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+// lo word: start address and leading byte offset
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -120,7 +159,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1
-//   bits [49,52) base offset               bits [61,64) layout type (2 = SWIZZLE_128B)
+//   bits [49,52) base offset (always 0)    bits [61,64) layout type (2 = SWIZZLE_128B)
 // K-major operand : rows are 128 B (64 bf16 along K), 8-row groups SBO apart; LBO unused.
 // MN-major operand: rows are 128 B (64 bf16 along M/N), one row per K index, 8-row K groups
 //                   SBO apart, 64-element M/N atoms LBO apart.
@@ -131,7 +170,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>((saddr >> 7) & 0x7) << 49;
+  // base offset (bits 49-51) stays 0: the swizzle pattern is anchored at 1024-byte-aligned
+  // absolute shared-memory addresses (where TMA wrote it), so an operand window may start at any
+  // 128-byte row of a swizzled tile -- verified on hardware by tools/diag_swizzle.cu.
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }

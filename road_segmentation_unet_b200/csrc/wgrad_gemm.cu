@@ -103,10 +103,10 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     *pt_end = static_cast<int>(1LL * pix_tiles * (ks + 1) / p.ksplit);
   };
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
+    // (whole warp converged, one elected lane issues; see conv_gemm.cu)
+    uint32_t stage = 0, phase = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       int m_tile, n_tile, pt0, pt1;
       unit_range(unit, &m_tile, &n_tile, &pt0, &pt1);
@@ -115,32 +115,44 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       const AtomCoord a0 = decode_atom(p, atom0, chunks_total);
       const AtomCoord a1 = decode_atom(p, n_a == 2 ? atom0 + 1 : atom0, chunks_total);
       const int n0 = n_tile * p.BN;
+      const uint32_t tx_bytes = static_cast<uint32_t>(n_a + n_b_atoms) * box_bytes;
+      int img = pt0 / tiles_per_img;
+      int r = pt0 % tiles_per_img;
+      int ty = r / p.tiles_x, tx = r % p.tiles_x;
       for (int pt = pt0; pt < pt1; ++pt) {
-        const int img = pt / tiles_per_img;
-        const int r = pt % tiles_per_img;
-        const int y0 = (r / p.tiles_x) * p.TH, x0 = (r % p.tiles_x) * p.TW;
+        const int y0 = ty * p.TH, x0 = tx * p.TW;
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t dst = smem_base + stage * stage_bytes;
-        mbar_expect_tx(full_bar(stage), static_cast<uint32_t>(n_a + n_b_atoms) * box_bytes);
-        tma_load_4d(dst, &p.a_map[a0.src], full_bar(stage), a0.chunk * 64, x0 + a0.dx, y0 + a0.dy,
-                    img);
-        if (n_a == 2)
-          tma_load_4d(dst + kBoxBytes, &p.a_map[a1.src], full_bar(stage), a1.chunk * 64,
-                      x0 + a1.dx, y0 + a1.dy, img);
-        for (int j = 0; j < n_b_atoms; ++j)
-          tma_load_4d(dst + (2 + j) * kBoxBytes, &p.b_map, full_bar(stage), n0 + j * 64,
-                      x0 + p.b_off_x, y0 + p.b_off_y, img);
-        if (++stage == stages) {
+        if (elect_one()) {
+          const uint32_t dst = smem_base + stage * stage_bytes;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, tx_bytes);
+          tma_load_4d(dst, &p.a_map[a0.src], fb, a0.chunk * 64, x0 + a0.dx, y0 + a0.dy, img);
+          if (n_a == 2)
+            tma_load_4d(dst + kBoxBytes, &p.a_map[a1.src], fb, a1.chunk * 64, x0 + a1.dx, y0 + a1.dy,
+                        img);
+          for (int j = 0; j < n_b_atoms; ++j)
+            tma_load_4d(dst + (2 + j) * kBoxBytes, &p.b_map, fb, n0 + j * 64, x0 + p.b_off_x,
+                        y0 + p.b_off_y, img);
+        }
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(stages)) {
           stage = 0;
           phase ^= 1u;
         }
+        if (++tx == p.tiles_x) {
+          tx = 0;
+          if (++ty == p.tiles_y) {
+            ty = 0;
+            ++img;
+          }
+        }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, true, true);
-    int stage = 0;
-    uint32_t phase = 0;
+    const uint32_t hi = desc_hi_sw128(1024u);
+    uint32_t stage = 0, phase = 0;
     uint32_t acc_it = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++acc_it) {
       int m_tile, n_tile, pt0, pt1;
@@ -150,26 +162,30 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kWgAccStride;
-      uint32_t first = 1;
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * stage_bytes;
-        const uint32_t b_addr = a_addr + 2 * kBoxBytes;
-        for (int j = 0; j < mma_per_tile; ++j) {
-          // 16 pixels (K) per instruction = 16 rows of 128 B = 2 KiB further into every atom
-          const uint64_t adesc = make_smem_desc_sw128(a_addr + j * 2048, kBoxBytes, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(b_addr + j * 2048, kBoxBytes, 1024);
-          umma_bf16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
-          first = 0;
+        if (elect_one()) {
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint32_t a_lo = desc_lo_sw128(a_addr, kBoxBytes);
+          const uint32_t b_lo = desc_lo_sw128(a_addr + 2 * kBoxBytes, kBoxBytes);
+          const uint32_t first = pt != pt0 ? 1u : 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // 16 pixels (K) per instruction = 16 rows of 128 B = 2 KiB further into every atom
+            if (j < mma_per_tile)
+              umma_bf16_lohi(d_tmem, a_lo + j * 128u, hi, b_lo + j * 128u, hi, idesc, j != 0 ? 1u : first);
+          }
+          umma_commit(empty_bar(stage));
         }
-        umma_commit(empty_bar(stage));
-        if (++stage == stages) {
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(stages)) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(tfull_bar(acc));
+      if (elect_one()) umma_commit(tfull_bar(acc));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: atomics to fp32
@@ -208,6 +224,8 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   if (warp == 2) tmem_dealloc(tmem_base, kWgTmemCols);
 }
 
+int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_done);  // wgrad_halo.cu
+
 }  // namespace rsu
 
 using namespace rsu;
@@ -221,6 +239,24 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   if (d->H < 1 || d->W < 1 || d->N_img < 1) return set_error(RSU_EINVAL, "empty pixel grid");
   if (reinterpret_cast<uintptr_t>(d->out) & 15)
     return set_error(RSU_EALIGN, "wgrad output must be 16-byte aligned");
+
+  if (d->bias_done_host) *d->bias_done_host = 0;
+  // (thresholds from the per-layer A/B table, profiles/r1_layers_ab.md; the halo kernel also
+  // produces the bias gradient, which is counted in its favour)
+  int chunks_all = 0;
+  for (int s = 0; s < d->n_src && s < kMaxSrc; ++s) chunks_all += d->src[s].C / 64;
+  const bool want_halo =
+      d->algo == 2 || (d->algo == 0 && d->n_taps == 9 && d->H >= 64 && d->W >= 64 && chunks_all <= 4 &&
+                       (d->grad.C <= 128 || (d->grad.C <= 256 && d->H >= 180)));
+  if (want_halo) {
+    int bias_done = 0;
+    const int rc = launch_wgrad_halo(d, stream, &bias_done);
+    if (rc >= 0) {
+      if (rc == RSU_OK && d->bias_done_host) *d->bias_done_host = bias_done;
+      return rc;
+    }
+    if (d->algo == 2) return set_error(RSU_EINVAL, "shape not eligible for the halo-tile kernel");
+  }
 
   WgradParams p;
   memset(&p, 0, sizeof(p));

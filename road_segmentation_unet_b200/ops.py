@@ -69,9 +69,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+ALGO_AUTO, ALGO_PER_TAP, ALGO_HALO = 0, 1, 2
+
+
 def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None, accumulate=False,
-              shuffle_cout=0, grid_hw=None):
-    """Generic implicit GEMM (rsu_conv_gemm).  srcs: list of (tensor_or_View, off_y, off_x)."""
+              shuffle_cout=0, grid_hw=None, algo=ALGO_AUTO):
+    """Generic implicit GEMM (rsu_conv_gemm).  srcs: list of (tensor_or_View, off_y, off_x).
+    algo: 0 = library's choice, 1 = one TMA box per tap, 2 = halo tile shared by all taps."""
     d = ConvGemmDesc()
     d.n_src = len(srcs)
     for i, (t, oy, ox) in enumerate(srcs):
@@ -95,11 +99,14 @@ def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None,
         d.mask = _ptr(mask)
         d.mask_sn, d.mask_sy, d.mask_sx = mask.stride()[:3]
     d.accumulate = int(accumulate)
+    d.algo = int(algo)
     _timed("conv_gemm", call, "rsu_conv_gemm", C.byref(d))
 
 
-def wgrad_gemm(srcs, taps, grad, grad_off, out, grid_hw):
-    """Generic weight-gradient GEMM (rsu_wgrad_gemm); out: fp32 [rows, Cout], pre-zeroed."""
+def wgrad_gemm(srcs, taps, grad, grad_off, out, grid_hw, bias_grad=None, algo=ALGO_AUTO):
+    """Generic weight-gradient GEMM (rsu_wgrad_gemm); out: fp32 [rows, Cout], pre-zeroed.
+    bias_grad (fp32 [Cout], accumulated into) is produced by the halo-tile kernel for free; the
+    return value tells whether it was (False: the caller still has to run bias_grad())."""
     d = WgradDesc()
     d.n_src = len(srcs)
     for i, (t, oy, ox) in enumerate(srcs):
@@ -114,7 +121,12 @@ def wgrad_gemm(srcs, taps, grad, grad_off, out, grid_hw):
     d.N_img = g.N
     d.out = _ptr(out)
     d.ldo = out.stride(0)
+    d.bias_grad = _ptr(bias_grad)
+    done = C.c_int(0)
+    d.bias_done_host = C.pointer(done)
+    d.algo = int(algo)
     _timed("wgrad_gemm", call, "rsu_wgrad_gemm", C.byref(d))
+    return bool(done.value)
 
 
 # ------------------------------------------------------------------ weight packing
@@ -133,21 +145,23 @@ def cast_bf16(src, out):
 
 
 # ------------------------------------------------------------------ conv 3x3 (unet.py:34-45,88-91)
-def conv3x3_fwd(srcs, w_fwd, bias, out, dilation=1, relu=True):
+def conv3x3_fwd(srcs, w_fwd, bias, out, dilation=1, relu=True, algo=ALGO_AUTO):
     """srcs: [(tensor, off_y, off_x)] in concat order; out [N,Ho,Wo,Cout] bf16."""
-    conv_gemm(srcs, conv_taps(dilation), w_fwd, out, out.shape[3], bias=bias, relu=relu)
+    conv_gemm(srcs, conv_taps(dilation), w_fwd, out, out.shape[3], bias=bias, relu=relu, algo=algo)
 
 
-def conv3x3_dgrad(dz, w_dgrad, dx_window, dilation=1, mask=None, accumulate=False):
+def conv3x3_dgrad(dz, w_dgrad, dx_window, dilation=1, mask=None, accumulate=False, algo=ALGO_AUTO):
     """dx_window[u,v] = sum_taps dz[u - ky*d, v - kx*d] W[ky,kx]^T over the touched input window
     (extent = dz extent + 2*dilation); optional fused ReLU mask / accumulation."""
     conv_gemm([(dz, 0, 0)], conv_taps(dilation, -1), w_dgrad, dx_window, dx_window.shape[3],
-              mask=mask, accumulate=accumulate)
+              mask=mask, accumulate=accumulate, algo=algo)
 
 
-def conv3x3_wgrad(srcs, dz, dw, dilation=1):
-    """dw fp32 [9*Cin_total, Cout] (HWIO), pre-zeroed; srcs as in conv3x3_fwd."""
-    wgrad_gemm(srcs, conv_taps(dilation), dz, (0, 0), dw, (dz.shape[1], dz.shape[2]))
+def conv3x3_wgrad(srcs, dz, dw, dilation=1, bias_grad=None, algo=ALGO_AUTO):
+    """dw fp32 [9*Cin_total, Cout] (HWIO), pre-zeroed; srcs as in conv3x3_fwd.  Returns True when
+    bias_grad was filled by the same kernel."""
+    return wgrad_gemm(srcs, conv_taps(dilation), dz, (0, 0), dw, (dz.shape[1], dz.shape[2]),
+                      bias_grad=bias_grad, algo=algo)
 
 
 # ------------------------------------------------------------------ conv2d_transpose (unet.py:67)

@@ -440,8 +440,9 @@ class UNet:
         """wgrad + bias grad (+ dgrad) of one 3x3 convolution."""
         self._tag(conv.name)
         g = lambda n: self.var(conv.name + "/" + n, "grads")
-        ops.conv3x3_wgrad(srcs, dz, g("kernel").view(-1, conv.cout), dilation=conv.dilation)
-        ops.bias_grad(dz, g("bias"))
+        if not ops.conv3x3_wgrad(srcs, dz, g("kernel").view(-1, conv.cout), dilation=conv.dilation,
+                                 bias_grad=g("bias")):
+            ops.bias_grad(dz, g("bias"))
         if need_dx:
             ops.conv3x3_dgrad(dz, conv.w_dgrad, dx, dilation=conv.dilation, mask=mask,
                               accumulate=accumulate)

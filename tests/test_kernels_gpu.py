@@ -339,3 +339,84 @@ def test_first_layer_via_im2col(ops):
     ops.conv_gemm([(col, 0, 0)], [(0, 0)], wp, out, cout, bias=dev(b, torch.float32), relu=True)
     ref = torch.relu(O.conv2d_valid(torch.tensor(bf(img - 0.5)), torch.tensor(w), torch.tensor(b))).numpy()
     assert rel_err(out.float().cpu().numpy(), ref) < 6e-3
+
+
+# ------------------------------------------------------------------ halo-tile kernels (algo = 2)
+HALO_FWD_CASES = [
+    # (N, H, srcs [(extent, channels, crop)], Cout, dilation)
+    (2, 40, [(40, 64, 0)], 64, 1),            # resident weights, MT = 2, ragged 38 x 38 output
+    (1, 70, [(70, 64, 0)], 128, 1),           # resident weights BN = 128 (MT = 1)
+    (2, 45, [(45, 128, 0)], 128, 2),          # streaming weights, dilation 2, two K chunks
+    (1, 36, [(44, 64, 4), (40, 64, 2), (36, 64, 0)], 64, 1),   # fused crop + concat, 3 sources
+    (1, 50, [(50, 64, 0)], 192, 1),           # three N tiles of 64, one per resident CTA group
+    (3, 18, [(18, 64, 0)], 64, 1),            # exactly one 16-row block (MT = 1)
+]
+
+
+@pytest.mark.parametrize("case", HALO_FWD_CASES)
+def test_conv3x3_fwd_halo(ops, case):
+    n, t, srcs, cout, d = case
+    rs = np.random.RandomState(21)
+    xs = [bf(rs.randn(n, e, e, c).astype(np.float32)) for e, c, _ in srcs]
+    cin = sum(c for _, c, _ in srcs)
+    w = bf((rs.randn(3, 3, cin, cout) / np.sqrt(9 * cin)).astype(np.float32))
+    b = rs.randn(cout).astype(np.float32)
+    ho = t - 2 * d
+    cat = torch.cat([O.center_crop(torch.tensor(x), t) for x in xs], dim=3)
+    ref = torch.relu(O.conv2d_valid(cat, torch.tensor(w), torch.tensor(b), d)).numpy()
+    outs = []
+    for algo in (ops.ALGO_HALO, ops.ALGO_PER_TAP):
+        out = torch.full((n, ho, ho, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+        ops.conv3x3_fwd([(dev(x), crop, crop) for x, (_, _, crop) in zip(xs, srcs)], pack_fwd(ops, w),
+                        dev(b, torch.float32), out, dilation=d, algo=algo)
+        outs.append(out.float().cpu().numpy())
+        assert rel_err(outs[-1], ref) < 6e-3, algo
+    # same products, same fp32 accumulation order over K up to the tap/chunk interleave
+    assert rel_err(outs[0], outs[1]) < 3e-3
+
+
+@pytest.mark.parametrize("case", [(2, 38, 64, 64, 1), (1, 41, 128, 64, 2), (1, 36, 64, 192, 1)])
+def test_conv3x3_dgrad_halo(ops, case):
+    """Data gradient through the halo kernel: negative tap offsets, zero-filled out-of-range reads,
+    fused ReluGrad mask and accumulation into a strided window."""
+    n, h, cin, cout, d = case
+    rs = np.random.RandomState(22)
+    x = torch.tensor(bf(rs.randn(n, h, h, cin).astype(np.float32)), requires_grad=True)
+    w = bf((rs.randn(3, 3, cin, cout) / np.sqrt(9 * cin)).astype(np.float32))
+    ho = h - 2 * d
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    O.conv2d_valid(x, torch.tensor(w), None, d).backward(torch.tensor(dz))
+    mask_src = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    ref = x.grad.numpy() * (mask_src > 0)
+    out = torch.zeros(n, h, h, cin, dtype=torch.bfloat16, device="cuda")
+    ops.conv3x3_dgrad(dev(dz), pack_dgrad(ops, w), out, dilation=d, mask=dev(mask_src), algo=ops.ALGO_HALO)
+    assert rel_err(out.float().cpu().numpy(), ref) < 6e-3
+    big = torch.ones(n, h + 6, h + 6, cin, dtype=torch.bfloat16, device="cuda")
+    win = big[:, 2:2 + h, 4:4 + h, :]
+    ops.conv3x3_dgrad(dev(dz), pack_dgrad(ops, w), win, dilation=d, accumulate=True, algo=ops.ALGO_HALO)
+    ref2 = np.ones((n, h + 6, h + 6, cin), dtype=np.float32)
+    ref2[:, 2:2 + h, 4:4 + h, :] += x.grad.numpy()
+    assert rel_err(big.float().cpu().numpy(), ref2) < 8e-3
+
+
+@pytest.mark.parametrize("case", [(2, 40, [(40, 64, 0)], 64, 1), (1, 52, [(52, 128, 0)], 128, 2),
+                                  (2, 30, [(38, 128, 4), (30, 64, 0)], 64, 1), (1, 33, [(33, 64, 0)], 256, 1)])
+def test_conv3x3_wgrad_halo(ops, case):
+    """Weight gradient of all nine taps from one halo tile, with BiasAddGrad from the spare atom."""
+    n, t, srcs, cout, d = case
+    rs = np.random.RandomState(23)
+    xs = [bf(rs.randn(n, e, e, c).astype(np.float32)) for e, c, _ in srcs]
+    cin = sum(c for _, c, _ in srcs)
+    ho = t - 2 * d
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    w = torch.zeros(3, 3, cin, cout, requires_grad=True)
+    cat = torch.cat([O.center_crop(torch.tensor(x), t) for x in xs], dim=3)
+    O.conv2d_valid(cat, w, None, d).backward(torch.tensor(dz))
+    ref = w.grad.numpy().reshape(9 * cin, cout)
+    out = torch.zeros(9 * cin, cout, dtype=torch.float32, device="cuda")
+    db = torch.zeros(cout, dtype=torch.float32, device="cuda")
+    done = ops.conv3x3_wgrad([(dev(x), crop, crop) for x, (_, _, crop) in zip(xs, srcs)], dev(dz), out,
+                             dilation=d, bias_grad=db, algo=ops.ALGO_HALO)
+    assert done
+    assert rel_err(out.cpu().numpy(), ref) < 2e-3
+    assert rel_err(db.cpu().numpy(), dz.sum(axis=(0, 1, 2))) < 2e-3

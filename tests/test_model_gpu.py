@@ -132,8 +132,9 @@ def test_train_step_parity(case):
     net.apply_gradients(0.01, 0.9)
     torch.cuda.synchronize()
     for name in live:  # delta_w = -lr * (0.9 * 0 + g): exactly the device's own gradient
-        dw = net.var(name).cpu().numpy() - params[name]
-        assert rel(dw, -0.01 * g_dev[name]) < 1e-3, name
+        # w' = w - lr * acc evaluated in fp32: identical up to the rounding of the subtraction
+        want = params[name] - np.float32(0.01) * g_dev[name]
+        assert np.allclose(net.var(name).cpu().numpy(), want, rtol=3e-7, atol=1e-9), name
         assert rel(net.var(name, "momentum").cpu().numpy(), g_dev[name]) < 1e-6, name
     assert net.global_step == 1
 
@@ -200,12 +201,47 @@ def test_backward_per_layer_teacher_forced(case):
                                            want_acts=True, storage="bf16")
     net = unet.UNet(L, root, dil, B, S, params=params)
     net.grads.zero_()
-    net.forward(torch.tensor(X).cuda(), torch.tensor(labels).cuda(), keep=1.0)
+    lab_dev = torch.tensor(labels).cuda()
+    net.forward(torch.tensor(X).cuda(), lab_dev, keep=1.0)
     torch.cuda.synchronize()
     f = net.f
 
     def a_val(name):
         return acts[name].detach().numpy()
+
+    # Teacher forcing of the forward state too: every saved activation is overwritten with the
+    # oracle's (bf16-storage, hence exactly representable) value after checking that the device's
+    # own forward agrees with it, so ReLU masks and pooling arg-maxes are identical on both sides
+    # and each backward kernel is compared on identical operands.
+    def force(buf, name, crop=None):
+        ref = a_val(name)
+        if crop is not None:
+            o, t = crop
+            ref = ref[:, o:o + t, o:o + t, :]
+        assert rel(buf.float().cpu().numpy(), ref) < TOL, name
+        buf.copy_(torch.tensor(np.ascontiguousarray(ref)).cuda().to(torch.bfloat16))
+        assert np.array_equal(buf.float().cpu().numpy(), ref), name  # bf16-exact
+
+    for i in range(L):
+        force(net.A1[i], "conv_%d/relu1" % i)
+        force(net.A2[i], "conv_%d/relu2" % i)
+        if i < L - 1:
+            force(net.Pool[i], "pool_%d" % i)
+            if dil:
+                t_i, o_i = net.up_size[L - 2 - i], net.dil_off[i]
+                force(net.D1[i], "conv_dilut_%d/relu1" % i, (o_i, t_i + 4))
+                force(net.D2[i], "conv_dilut_%d/relu2" % i, (o_i, t_i))
+    for j in range(L - 1):
+        force(net.U[j], "up_conv_%d" % j)
+        force(net.C1[j], "conv_%d/relu1" % (L + j))
+        force(net.C2[j], "conv_%d/relu2" % (L + j))
+    # head on the forced activation (loss + gradients that leave it)
+    net.grads.zero_()
+    net.loss.zero_()
+    ops.head(net._last, net.var("weight_output/kernel").view(-1, 2), net.var("weight_output/bias"),
+             labels=lab_dev, probs=net.probs, loss=net.loss, dz=net.dC2[L - 2],
+             dw=net.var("weight_output/kernel", "grads").view(-1, 2),
+             db=net.var("weight_output/bias", "grads"))
 
     def a_grad(name, masked=True, crop=None):
         g = acts[name].grad.numpy()
@@ -311,9 +347,11 @@ def test_backward_per_layer_teacher_forced(case):
             y = a_val(n2)
             win = y.reshape(B, y.shape[1] // 2, 2, y.shape[2] // 2, 2, y.shape[3])
             mx = win.max(axis=(2, 4), keepdims=True)
-            uniq = np.broadcast_to((win == mx).sum(axis=(2, 4), keepdims=True) == 1, win.shape).reshape(y.shape)
-            uniq = uniq & same_mask(net.A2[i], n2) & (got(net.A2[i]) == y)
-            assert uniq.mean() > 0.9
+            # (an all-zero window is a 4-way tie too, but ReluGrad zeroes it on both sides)
+            uniq = np.broadcast_to(((win == mx).sum(axis=(2, 4), keepdims=True) == 1) | (mx == 0),
+                                   win.shape).reshape(y.shape)
+            assert np.array_equal(got(net.A2[i]), y)
+            assert uniq.mean() > 0.97  # positive bf16 ties are rare but do occur
             check("dZ(skip) " + n2, got(net.dA2[i])[uniq], a_grad(n2)[uniq])
         net.grads.zero_()
         put(net.dA2[i], a_grad(n2))

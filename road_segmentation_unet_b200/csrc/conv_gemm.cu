@@ -180,6 +180,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           bias_t[j] = __ldg(p.bias + (p.shuffle_cout > 0 ? n % p.shuffle_cout : n));
         }
       }
+      // ReLU-gradient mask bits of this tile, fetched while the MMAs are still running
+      uint32_t mbits[2][4];
+      if (p.mask != nullptr) {
+        const __nv_bfloat16* mpx = p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + n0;
+        load_mask_bits4(mpx, p.BN / 32, valid, mbits[0]);
+        load_mask_bits4(mpx + 128, p.BN / 32 - 4, valid, mbits[1]);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       named_bar_sync(1, 128);  // bias_t visible to the 4 epilogue warps
@@ -211,18 +218,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (p.mask != nullptr) {
-            const uint4* mp = reinterpret_cast<const uint4*>(
-                p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + n);
+            uint32_t mb = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 mv = __ldg(mp + q);
-              const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+            for (int c = 0; c < 8; ++c)
+              if (c == ch) mb = mbits[c >> 2][c & 3];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (!(bf16_lo(w[e]) > 0.f)) v[q * 8 + 2 * e] = 0.f;
-                if (!(bf16_hi(w[e]) > 0.f)) v[q * 8 + 2 * e + 1] = 0.f;
-              }
-            }
+            for (int j = 0; j < 32; ++j)
+              if (!((mb >> j) & 1u)) v[j] = 0.f;
           }
           uint4* op = reinterpret_cast<uint4*>(p.out + off);
           if (p.accumulate) {

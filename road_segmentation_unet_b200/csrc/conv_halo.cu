@@ -56,6 +56,12 @@ struct ConvHaloParams {
   const __nv_bfloat16* mask;
   long long mask_sn, mask_sy, mask_sx;
   int accumulate;
+  // Coalesced epilogue (used unless accumulate): 64-channel x 128-pixel blocks are staged in
+  // shared memory (128-byte swizzle) and written with TMA stores; the ReLU-gradient mask blocks
+  // arrive the same way (TMA loads, two blocks ahead).
+  int tma_epilogue;
+  CUtensorMap out_map;   // 4-D (C, W, H, N) bf16, box {64, 8, 16, 1}
+  CUtensorMap mask_map;  // same geometry over the mask tensor
 };
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
@@ -66,7 +72,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   const int lane = threadIdx.x & 31;
 
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.BN) * 128u;
-  const uint32_t b_base = smem_base + p.stages_a * p.a_stage_bytes;
+  const uint32_t b_base = smem_base + p.stages_a * p.a_stage_bytes +
+                          (p.tma_epilogue ? (p.mask != nullptr ? 4u : 2u) * 16384u : 0u);
   const uint32_t bar_base = b_base + p.stages_b * b_stage_bytes;
   // barriers: a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] tfull[2] tempty[2]
   const int SA = p.stages_a, SB = p.stages_b;
@@ -78,6 +85,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
   const uint32_t bias_base = tmem_slot + 16u;  // float [2][128]
+  // epilogue staging: out[2] (16 KiB each) then mask[2]; placed before the barriers, 1024-aligned
+  const uint32_t stg_base = b_base - (p.tma_epilogue ? (p.mask != nullptr ? 4u : 2u) * 16384u : 0u);
+  const uint32_t mfull_base = bias_base + 2u * 128u * 4u;  // mask_full[2] mbarriers
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -86,6 +96,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&p.a_map[s]);
     tma_prefetch_desc(&p.b_map);
+    if (p.tma_epilogue) {
+      tma_prefetch_desc(&p.out_map);
+      if (p.mask != nullptr) tma_prefetch_desc(&p.mask_map);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < SA; ++s) {
@@ -99,6 +113,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);
+      mbar_init(mfull_base + 8u * a, 1);
     }
     fence_mbar_init();
   }
@@ -273,8 +288,132 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       __syncwarp();
       first = false;
     }
+  } else if (warp >= 4 && p.tma_epilogue) {
+    // ------------------------------------------------------------ epilogue (TMA stores)
+    // A "block" is one 64-channel column block of one 16-row accumulator: 128 rows x 128 B in
+    // shared memory, row m = pixel (m / 8, m % 8), 16-byte chunk c stored at c ^ (m & 7).
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const bool leader = et == 0;
+    const bool has_mask = p.mask != nullptr;
+    const int cbs = p.BN / 64;               // column blocks per accumulator
+    const int bpu = p.MT * cbs;              // blocks per unit
+    const uint32_t out_stg = stg_base;
+    const uint32_t mask_stg = stg_base + 2u * 16384u;
+    const uint32_t row_off = static_cast<uint32_t>(m) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(m & 7);
+    // block q (counted over this CTA's whole life) -> tensor coordinates of its 8 x 16 pixel box
+    auto block_coords = [&](long long q, int* c0, int* bx, int* by, int* bimg) -> bool {
+      const long long ord = q / bpu;
+      const int rem = static_cast<int>(q % bpu);
+      const long long u = u_begin + ord * u_step;
+      if (u >= u_end) return false;
+      int n_tile, tx, ty, img;
+      decode(static_cast<int>(u), &n_tile, &tx, &ty, &img);
+      const int mt = rem / cbs, cb = rem % cbs;
+      *c0 = n_tile * p.BN + cb * 64;
+      *bx = tx * kHaloTW;
+      *by = (ty * p.MT + mt) * kHaloTH;
+      *bimg = img;
+      return true;
+    };
+    auto issue_mask = [&](long long q) {
+      int c0, bx, by, bimg;
+      if (block_coords(q, &c0, &bx, &by, &bimg)) {
+        const uint32_t bar = mfull_base + 8u * static_cast<uint32_t>(q & 1);
+        mbar_expect_tx(bar, 16384u);
+        tma_load_4d(mask_stg + static_cast<uint32_t>(q & 1) * 16384u, &p.mask_map, bar, c0, bx, by, bimg);
+      }
+    };
+    if (has_mask && leader) {
+      issue_mask(0);
+      issue_mask(1);
+    }
+    long long q = 0;
+    uint32_t acc_it = 0;
+    for (int u = u_begin; u < u_end; u += u_step, ++acc_it) {
+      const uint32_t acc = acc_it & 1u;
+      const uint32_t acc_phase = (acc_it >> 1) & 1u;
+      int n_tile, tx, ty, img;
+      decode(u, &n_tile, &tx, &ty, &img);
+      const int n0 = n_tile * p.BN;
+      float* bias_t = bias_s + acc * 128;
+      if (p.bias != nullptr) {
+        for (int j = et; j < p.BN; j += 128) bias_t[j] = __ldg(p.bias + n0 + j);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      // (bias_t is published by the first named barrier of the first block below)
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
+                               acc * acc_set_cols + mt * p.BN;
+        for (int cb = 0; cb < cbs; ++cb, ++q) {
+          const uint32_t buf = static_cast<uint32_t>(q & 1);
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + cb * 64, r0);
+          tmem_ld32(t_row + cb * 64 + 32, r1);
+          if (has_mask) mbar_wait(mfull_base + 8u * buf, static_cast<uint32_t>((q >> 1) & 1));
+          tmem_ld_wait();
+          // barrier A: the leader has seen the store that last used out_stg[buf] finish reading,
+          // and (first block of a unit) every warp's bias_t writes are visible
+          named_bar_sync(1, 128);
+          uint4 packed[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(h == 0 ? r0[j] : r1[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += bias_t[cb * 64 + h * 32 + j];
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (has_mask) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 mv = ld_shared_v4(mask_stg + buf * 16384u + row_off +
+                                              ((static_cast<uint32_t>(h * 4 + c) ^ swz) << 4));
+                const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16_lo(w[e]) > 0.f)) v[c * 8 + 2 * e] = 0.f;
+                  if (!(bf16_hi(w[e]) > 0.f)) v[c * 8 + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              packed[h * 4 + c].x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]);
+              packed[h * 4 + c].y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+              packed[h * 4 + c].z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
+              packed[h * 4 + c].w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            st_shared_v4(out_stg + buf * 16384u + row_off + ((static_cast<uint32_t>(c) ^ swz) << 4), packed[c]);
+          fence_proxy_async();
+          named_bar_sync(2, 128);  // barrier B: block complete in smem, mask block fully consumed
+          if (leader) {
+            tma_store_4d(&p.out_map, out_stg + buf * 16384u, n0 + cb * 64, tx * kHaloTW,
+                         (ty * p.MT + mt) * kHaloTH, img);
+            tma_store_commit();
+            if (has_mask) issue_mask(q + 2);
+            tma_store_wait_read<1>();  // the other staging buffer is free again
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (leader) tma_store_wait_all<0>();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue (direct stores)
     const int wq = warp & 3;
     const int m = wq * 32 + lane;
     const int ly = m >> 3, lx = m & 7;
@@ -291,6 +430,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       float* bias_t = bias_s + acc * 128;
       if (p.bias != nullptr) {
         for (int j = et; j < p.BN; j += 128) bias_t[j] = __ldg(p.bias + n0 + j);
+      }
+      // ReLU-gradient mask bits of this unit, fetched while the MMAs are still running
+      uint32_t mbits[2][4];
+      if (p.mask != nullptr) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int y = (ty * p.MT + mt) * kHaloTH + ly;
+          const bool valid = mt < p.MT && y < p.H_out && x < p.W_out;
+          load_mask_bits4(p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + n0, p.BN / 32,
+                          valid, mbits[mt]);
+        }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -320,18 +470,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (p.mask != nullptr) {
-              const uint4* mp = reinterpret_cast<const uint4*>(
-                  p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + n);
+              const uint32_t mb = mt == 0 ? (ch == 0 ? mbits[0][0] : ch == 1 ? mbits[0][1] : ch == 2 ? mbits[0][2] : mbits[0][3])
+                                          : (ch == 0 ? mbits[1][0] : ch == 1 ? mbits[1][1] : ch == 2 ? mbits[1][2] : mbits[1][3]);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 mv = __ldg(mp + q);
-                const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (!(bf16_lo(w[e]) > 0.f)) v[q * 8 + 2 * e] = 0.f;
-                  if (!(bf16_hi(w[e]) > 0.f)) v[q * 8 + 2 * e + 1] = 0.f;
-                }
-              }
+              for (int j = 0; j < 32; ++j)
+                if (!((mb >> j) & 1u)) v[j] = 0.f;
             }
             uint4* op = reinterpret_cast<uint4*>(p.out + off);
             if (p.accumulate) {
@@ -387,7 +530,8 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
   int chunks_total = 0;
   for (int s = 0; s < d->n_src; ++s) chunks_total += d->src[s].C / 64;
   const int num_k = d->n_taps * chunks_total;
-  const int smem_budget = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers, bias*/;
+  const int smem_max = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers, bias*/;
+  const int stg_full = (d->mask ? 4 : 2) * 16384;  // staging of the TMA epilogue
 
   ConvHaloParams p;
   memset(&p, 0, sizeof(p));
@@ -398,26 +542,37 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
   auto a_stage = [&](int mt) {
     return static_cast<uint32_t>(((p.Wh * (kHaloTH * mt + span_y) * 128) + 1023) & ~1023);
   };
-  // Candidate configurations in order of preference:
-  //   resident weights with MT = 2, resident with MT = 1, streaming with MT = 2.
+  // Candidate configurations in order of preference: resident weights (TMA epilogue, MT = 2 / 1;
+  // then direct-store epilogue, which needs no staging buffers, MT = 2 / 1), else streaming
+  // weights with MT = 2 and the TMA epilogue.
   const int b_stage = p.BN * 128;
   const int sms = num_sms();
   bool chosen = false;
-  if (p.n_tiles_n <= sms) {
-    for (int mt = 2; mt >= 1 && !chosen; --mt) {
-      if (kHaloTH * mt > d->H_out + kHaloTH - 1 && mt == 2) continue;  // a single block row suffices
-      const int need = num_k * b_stage + 2 * static_cast<int>(a_stage(mt));
-      if (num_k <= kMaxBStages && need <= smem_budget) {
-        p.resident = 1;
-        p.MT = mt;
-        p.stages_b = num_k;
-        p.stages_a = (smem_budget - num_k * b_stage) / static_cast<int>(a_stage(mt));
-        if (p.stages_a > 4) p.stages_a = 4;
-        chosen = true;
+  bool tma_epi = !d->accumulate;
+  int stg_bytes = 0, smem_budget = smem_max;
+  if (p.n_tiles_n <= sms && num_k <= kMaxBStages) {
+    for (int epi = d->accumulate ? 0 : 1; epi >= 0 && !chosen; --epi) {
+      const int budget = smem_max - (epi ? stg_full : 0);
+      for (int mt = 2; mt >= 1 && !chosen; --mt) {
+        if (mt == 2 && d->H_out <= kHaloTH) continue;  // a single block row suffices
+        const int need = num_k * b_stage + 2 * static_cast<int>(a_stage(mt));
+        if (need <= budget) {
+          p.resident = 1;
+          p.MT = mt;
+          p.stages_b = num_k;
+          p.stages_a = (budget - num_k * b_stage) / static_cast<int>(a_stage(mt));
+          if (p.stages_a > 4) p.stages_a = 4;
+          tma_epi = epi != 0;
+          stg_bytes = epi ? stg_full : 0;
+          smem_budget = budget;
+          chosen = true;
+        }
       }
     }
   }
   if (!chosen) {
+    stg_bytes = tma_epi ? stg_full : 0;
+    smem_budget = smem_max - stg_bytes;
     p.resident = 0;
     p.MT = (d->H_out > kHaloTH) ? 2 : 1;
     p.stages_a = 2;
@@ -464,9 +619,33 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
   p.mask_sy = d->mask_sy;
   p.mask_sx = d->mask_sx;
   p.accumulate = d->accumulate;
+  p.tma_epilogue = tma_epi ? 1 : 0;
+  if (tma_epi) {
+    rsu_view ov;
+    ov.ptr = d->out;
+    ov.C = d->Ntot;
+    ov.H = d->H_out;
+    ov.W = d->W_out;
+    ov.N = d->N_img;
+    ov.sn = d->out_sn;
+    ov.sy = d->out_sy;
+    ov.sx = d->out_sx;
+    ov.off_y = ov.off_x = 0;
+    int rc = encode_act_map(&p.out_map, ov, kHaloTW, kHaloTH);
+    if (rc) return rc;
+    if (d->mask) {
+      ov.ptr = d->mask;
+      ov.sn = d->mask_sn;
+      ov.sy = d->mask_sy;
+      ov.sx = d->mask_sx;
+      rc = encode_act_map(&p.mask_map, ov, kHaloTW, kHaloTH);
+      if (rc) return rc;
+    }
+  }
 
-  const int smem = 1024 + p.stages_a * static_cast<int>(p.a_stage_bytes) + p.stages_b * b_stage +
-                   8 * (2 * p.stages_a + 2 * p.stages_b + 4) + 16 + 2 * 128 * 4;
+  const int smem = 1024 + p.stages_a * static_cast<int>(p.a_stage_bytes) + stg_bytes +
+                   p.stages_b * b_stage + 8 * (2 * p.stages_a + 2 * p.stages_b + 4) + 16 +
+                   2 * 128 * 4 + 16 /*mask_full*/;
   static bool attr_set = false;
   if (!attr_set) {
     RSU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel,

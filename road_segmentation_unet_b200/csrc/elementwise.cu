@@ -231,61 +231,71 @@ __global__ void maxpool2x2_kernel(const uint4* __restrict__ in, int N, int H, in
 
 // MaxPoolGrad + crop-pad of the concat gradient + ReluGrad in one pass over the skip tensor
 // (unet.py:47-52, 70-85).  The pool gradient goes to the first maximum of each 2x2 window.
+// One thread owns one 2x2 window x 8 channels: Y and dZ are touched exactly once, and the two
+// horizontally adjacent pixels of a window are contiguous in NHWC, so a warp moves 1 KiB runs.
+// WINDOWED = false (no pool below, odd extents allowed): one thread per pixel x 8 channels.
+template <bool WINDOWED>
 __global__ void skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int W, int G,
                                  const uint4* __restrict__ dP, const __nv_bfloat16* __restrict__ dC,
                                  long long c_sn, long long c_sy, long long c_sx, int Hc, int Wc,
                                  int crop_y, int crop_x, uint4* __restrict__ dZ) {
-  const long long total = 1LL * N * H * W * G;
+  constexpr int S = WINDOWED ? 2 : 1;
+  const int Hw = H / S, Ww = W / S;
+  const long long total = 1LL * N * Hw * Ww * G;
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
        i += 1LL * gridDim.x * blockDim.x) {
     const int g = static_cast<int>(i % G);
     const long long p = i / G;
-    const int x = static_cast<int>(p % W);
-    const int y = static_cast<int>((p / W) % H);
-    const int n = static_cast<int>(p / (1LL * W * H));
-    float yv[8], gr[8];
-    unpack8(__ldg(Y + i), yv);
+    const int wx = static_cast<int>(p % Ww);
+    const int wy = static_cast<int>((p / Ww) % Hw);
+    const int n = static_cast<int>(p / (1LL * Ww * Hw));
+    float yv[S * S][8], gr[S * S][8];
+    long long idx[S * S];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) gr[e] = 0.f;
-    if (dP != nullptr) {
-      const int wy = y & ~1, wx = x & ~1;
-      const int my = y & 1, mx = x & 1;
-      const int pos = my * 2 + mx;  // position of this element in row-major window order
-      const long long wbase = ((1LL * n * H + wy) * W + wx) * G + g;
-      float w[4][8];
-      unpack8(__ldg(Y + wbase), w[0]);
-      unpack8(__ldg(Y + wbase + G), w[1]);
-      unpack8(__ldg(Y + wbase + 1LL * W * G), w[2]);
-      unpack8(__ldg(Y + wbase + 1LL * W * G + G), w[3]);
+    for (int q = 0; q < S * S; ++q) {
+      const int y = wy * S + q / S, x = wx * S + q % S;
+      idx[q] = ((1LL * n * H + y) * W + x) * G + g;
+      unpack8(__ldg(Y + idx[q]), yv[q]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gr[q][e] = 0.f;
+    }
+    if (WINDOWED && dP != nullptr) {
       float dp[8];
-      unpack8(__ldg(dP + ((1LL * n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * G + g), dp);
+      unpack8(__ldg(dP + i), dp);  // dP is [N, H/2, W/2, C]: same linear index as the window
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         int arg = 0;
-        float best = w[0][e];
+        float best = yv[0][e];
 #pragma unroll
-        for (int q = 1; q < 4; ++q)
-          if (w[q][e] > best) {
-            best = w[q][e];
+        for (int q = 1; q < S * S; ++q)
+          if (yv[q][e] > best) {
+            best = yv[q][e];
             arg = q;
           }
-        if (arg == pos) gr[e] = dp[e];
+#pragma unroll
+        for (int q = 0; q < S * S; ++q)
+          if (arg == q) gr[q][e] = dp[e];
       }
     }
     if (dC != nullptr) {
-      const int cy = y - crop_y, cx = x - crop_x;
-      if (cy >= 0 && cy < Hc && cx >= 0 && cx < Wc) {
-        float dc[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dC + n * c_sn + cy * c_sy + cx * c_sx) + g),
-                dc);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gr[e] += dc[e];
+      for (int q = 0; q < S * S; ++q) {
+        const int cy = wy * S + q / S - crop_y, cx = wx * S + q % S - crop_x;
+        if (cy >= 0 && cy < Hc && cx >= 0 && cx < Wc) {
+          float dc[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(dC + n * c_sn + cy * c_sy + cx * c_sx) + g), dc);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gr[q][e] += dc[e];
+        }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (!(yv[e] > 0.f)) gr[e] = 0.f;
-    dZ[i] = pack8(gr);
+    for (int q = 0; q < S * S; ++q) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (!(yv[q][e] > 0.f)) gr[q][e] = 0.f;
+      dZ[idx[q]] = pack8(gr[q]);
+    }
   }
 }
 
@@ -324,14 +334,27 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ v, long long 
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   const long long pixels = 1LL * N * H * W;
-  for (long long p = blockIdx.x * 1LL * k + lane; p < pixels; p += 1LL * gridDim.x * k) {
-    const int x = static_cast<int>(p % W);
-    const int y = static_cast<int>((p / W) % H);
-    const int n = static_cast<int>(p / (1LL * W * H));
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(v + n * sn + y * sy + x * sx) + g), f);
+  const long long stride = 1LL * gridDim.x * k;
+  for (long long p0 = blockIdx.x * 1LL * k + lane; p0 < pixels; p0 += 4 * stride) {
+    uint4 raw[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    for (int u = 0; u < 4; ++u) {  // four independent 16-byte loads in flight per thread
+      const long long p = p0 + u * stride;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (p < pixels) {
+        const int x = static_cast<int>(p % W);
+        const int y = static_cast<int>((p / W) % H);
+        const int n = static_cast<int>(p / (1LL * W * H));
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(v + n * sn + y * sy + x * sx) + g);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) atomicAdd(&sred[g * 8 + e], acc[e]);
@@ -593,12 +616,19 @@ int rsu_skip_grad(const void* Y, int N, int H, int W, int C, const void* dP, con
   if (dCrop && (dCrop->C != C || dCrop->N != N || (dCrop->sx % 8) || (dCrop->sy % 8) ||
                 (dCrop->sn % 8) || (reinterpret_cast<uintptr_t>(dCrop->ptr) & 15)))
     return set_error(RSU_EINVAL, "skip_grad: bad crop view");
-  const long long total = 1LL * N * H * W * (C / 8);
-  skip_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const uint4*>(Y), N, H, W, C / 8, static_cast<const uint4*>(dP),
-      dCrop ? static_cast<const __nv_bfloat16*>(dCrop->ptr) : nullptr, dCrop ? dCrop->sn : 0,
-      dCrop ? dCrop->sy : 0, dCrop ? dCrop->sx : 0, dCrop ? dCrop->H : 0, dCrop ? dCrop->W : 0,
-      crop_y, crop_x, static_cast<uint4*>(dZ));
+#define RSU_SKIP_ARGS                                                                          \
+  static_cast<const uint4*>(Y), N, H, W, C / 8, static_cast<const uint4*>(dP),                   \
+      dCrop ? static_cast<const __nv_bfloat16*>(dCrop->ptr) : nullptr, dCrop ? dCrop->sn : 0,    \
+      dCrop ? dCrop->sy : 0, dCrop ? dCrop->sx : 0, dCrop ? dCrop->H : 0, dCrop ? dCrop->W : 0,  \
+      crop_y, crop_x, static_cast<uint4*>(dZ)
+  if (dP) {
+    const long long total = 1LL * N * (H / 2) * (W / 2) * (C / 8);
+    skip_grad_kernel<true><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
+  } else {
+    const long long total = 1LL * N * H * W * (C / 8);
+    skip_grad_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
+  }
+#undef RSU_SKIP_ARGS
   return check_launch("skip_grad");
 }
 
@@ -625,7 +655,7 @@ int rsu_bias_grad(const rsu_view* v, float* out, void* stream) {
   if (k < 1) k = 1;
   const long long pixels = 1LL * v->N * v->H * v->W;
   long long blocks = (pixels + k - 1) / k;
-  const long long cap = 1LL * num_sms() * 8;
+  const long long cap = 1LL * num_sms() * 6;
   if (blocks > cap) blocks = cap;
   bias_grad_kernel<<<static_cast<int>(blocks), G * k, G * 8 * sizeof(float), (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(v->ptr), v->sn, v->sy, v->sx, v->N, v->H, v->W, G, k, out);

@@ -81,6 +81,41 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint3
       : "memory");
 }
 
+// TMA store of a shared-memory tile (bulk async group completion); elements outside the tensor
+// are clipped by the hardware, so ragged edge tiles need no store masks.
+__device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until at most N committed store groups still have to READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
@@ -191,6 +226,38 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ReLU-gradient mask of up to 4 x 32 consecutive bf16 channels of one pixel as bit words
+// (bit j of word c = element 32c + j > 0).  All 16-byte loads are issued before any is used, so
+// one call costs one memory latency; the epilogues call it while they wait for the accumulator.
+__device__ __forceinline__ void load_mask_bits4(const __nv_bfloat16* px, int n_chunks, bool valid,
+                                                uint32_t (&bits)[4]) {
+  uint4 raw[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      raw[c][q] = make_uint4(0, 0, 0, 0);
+      if (valid && c < n_chunks) raw[c][q] = __ldg(reinterpret_cast<const uint4*>(px + c * 32) + q);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {raw[c][q].x, raw[c][q].y, raw[c][q].z, raw[c][q].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // bf16 > 0  <=>  sign clear and magnitude non-zero (NaNs never occur in ReLU outputs)
+        const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
+        b |= ((lo - 1u) < 0x7FFFu ? 1u : 0u) << (q * 8 + 2 * e);
+        b |= ((hi - 1u) < 0x7FFFu ? 1u : 0u) << (q * 8 + 2 * e + 1);
+      }
+    }
+    bits[c] = b;
+  }
+}
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

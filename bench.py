@@ -266,6 +266,37 @@ def run_gpu(args):
     h2d = B * S * S * 3 * 4 + B * P * P
     d2h = B * P * P * 4 + 4
 
+    # ---- sliding-window ensemble prediction (BASELINE.json configs[2]) through the public API:
+    # one synthetic 604^2 image, stride 12, 6-way flip/rot90 ensemble = 2,166 patch forwards of the
+    # same model, patches sharded over the ranks, host image in / host mask out
+    predict = None
+    if not args.no_predict:
+        import contextlib
+        import io
+        opts.ensemble_prediction, opts.stride = True, 12
+        imgs = np.random.RandomState(2017).rand(args.predict_images, 604, 604, 3).astype(np.float32)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.predict(imgs[:, :400, :400])  # warm-up on a small crop (4 patches per variant)
+            barrier()
+            t0 = time.perf_counter()
+            masks = model.predict(imgs)
+            torch.cuda.synchronize()
+            pred_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([pred_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pred_s = float(t.item())
+        n_fwd = args.predict_images * 6 * 19 * 19
+        f_fwd = sum(unet.plan_flops(CFG["num_layers"], CFG["root_size"], CFG["dilated_layers"],
+                                    CFG["patch_size"]).values())
+        predict = {"value": masks.shape[0] * masks.shape[1] * masks.shape[2] / pred_s / 1e6,
+                   "unit": "Mpix/s", "seconds": pred_s, "patch_forwards_per_s": n_fwd / pred_s,
+                   "tflops": n_fwd * f_fwd / pred_s / 1e12,
+                   "config": "%d synthetic 604^2 image(s), stride 12, 6-way ensemble, %d patch forwards "
+                             "sharded over %d GPU(s), ConvolutionalModel.predict (host in / host out)"
+                             % (args.predict_images, n_fwd, world),
+                   "mask_mean": float(masks.mean())}
+
     # ---- roofline of the dominant kernel: CUDA events around every tcgen05 launch (same steps,
     # instrumented pass so that the headline region above stays free of event records)
     roof = None
@@ -339,7 +370,7 @@ def run_gpu(args):
                     "steps": ke, "api": "tf_aerial_images.ConvolutionalModel.train_batch (pinned host batch in, "
                                         "loss + probabilities read back every step)"},
             "gpu_launches": launches, "loss": loss_val, "clocks": clocks,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "predict": predict,
         }
         line.update(extra)
         print(json.dumps(line))
@@ -357,6 +388,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 32 = the named config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--quick", action="store_true", help="device-timed region only (for ncu runs)")
+    ap.add_argument("--no-predict", action="store_true", help="skip the sliding-window prediction leg")
+    ap.add_argument("--predict-images", type=int, default=1, help="604^2 images in the prediction leg")
     ap.add_argument("--dump-layers", default="", help="write the per-layer tcgen05 kernel timing table here")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -108,9 +108,23 @@ int rsu_pack_permute(const float* in, void* out, int T, int R, int C, const int*
 /* fp32 -> bf16 cast (transpose-conv forward weights keep TensorFlow's [kh][kw][Cout][Cin]). */
 int rsu_cast_bf16(const float* in, void* out, long long n, void* stream);
 
+/* All repacks of one optimizer step in one launch.  rsu_pack_plan validates a host job list,
+ * uploads the device table into caller-owned memory (rsu_pack_plan_bytes(n_jobs) bytes; done once,
+ * synchronous) and returns the grid size; rsu_pack_run launches it.  kind 0 = rsu_pack_transpose,
+ * 1 = rsu_pack_permute with the identity permutation, 2 = rsu_cast_bf16 (n = T*R*C). */
+typedef struct {
+  const float* in;
+  void* out;
+  int kind, T, R, C, ld;
+} rsu_pack_job;
+int rsu_pack_plan_bytes(int n_jobs);
+int rsu_pack_plan(const rsu_pack_job* jobs_host, int n_jobs, void* table_dev, int* total_blocks);
+int rsu_pack_run(const void* table_dev, int n_jobs, int total_blocks, void* stream);
+
 /* ---------------------------------------------------------------- fused elementwise ------- */
 /* color_space_adjust (unet.py:22-23) + optional dropout (unet.py:29-30) + im2col of the 3x3
- * (dilation d) neighbourhood into 64 bf16 channels (27 used, k = tap*3 + c):
+ * (dilation d) neighbourhood into 64 bf16 channels (k = tap*3 + c for k < 27, channel 27 = 1.0
+ * so that the weight-gradient GEMM also yields BiasAddGrad, channels 28..63 = 0):
  *   net0 = (img - 0.5) @ W1 + b1 ; out[n, y, x, tap*3+c] = net0[n, y+oy+dy*d, x+ox+dx*d, c] */
 int rsu_color_im2col(const float* img, int N, int S, const float* w1 /* device [3][3] */,
                      const float* b1 /* device [3] */, int dilation, int oy, int ox, int Ho, int Wo,
@@ -121,6 +135,19 @@ int rsu_color_im2col(const float* img, int N, int S, const float* w1 /* device [
 int rsu_color_im2col_bwd(const float* img, int N, int S, const void* dcol, int dilation, int oy,
                          int ox, int Ho, int Wo, float* dw1, float* db1, float keep,
                          unsigned long long seed, void* stream);
+
+/* First layer without dropout: color_space_adjust (unet.py:22-23) folded into the Cin = 3
+ * convolution that follows (unet.py:34, :42).  w: HWIO fp32 [3,3,3,cout], b [cout], w1 [3][3],
+ * b1 [3] (device).  Writes the packed bf16 GEMM operand w_packed [cout][64] (k = tap*3 + ci,
+ * zero padded) of the folded kernel W' = W1 . W and the folded bias b' = b + sum b1 . W. */
+int rsu_first_layer_fold(const float* w, const float* b, const float* w1, const float* b1, int cout,
+                         void* w_packed, float* bias_eff, void* stream);
+/* Backward of the folded first layer from gx = im2col(x - 0.5)^T dZ (fp32 [>=28][ldg], row
+ * tap*3 + ci; row 27 = column sums of dZ, produced by the constant-one column 27 that
+ * rsu_color_im2col writes): accumulates dw [3,3,3,cout] (Conv2DBackpropFilter), dbias [cout]
+ * (BiasAddGrad), dw1 [3][3] and db1 [3] (gradients of color_space_adjust). */
+int rsu_first_layer_grads(const float* gx, int ldg, const float* w, const float* w1, const float* b1,
+                          int cout, float* dw, float* dbias, float* dw1, float* db1, void* stream);
 
 /* 2x2/2 max-pool, NHWC bf16 (tf.layers.max_pooling2d, unet.py:52). */
 int rsu_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, void* stream);

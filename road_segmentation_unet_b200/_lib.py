@@ -39,6 +39,11 @@ class WgradDesc(C.Structure):
                 ("bias_done_host", C.POINTER(C.c_int)), ("algo", C.c_int)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("out", C.c_void_p), ("kind", C.c_int), ("T", C.c_int),
+                ("R", C.c_int), ("C", C.c_int), ("ld", C.c_int)]
+
+
 class RsuError(RuntimeError):
     pass
 
@@ -59,6 +64,11 @@ _SIGNATURES = {
     "rsu_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "rsu_color_im2col": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _ull, _vp]),
     "rsu_color_im2col_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _ull, _vp]),
+    "rsu_pack_plan_bytes": (_i, [_i]),
+    "rsu_pack_plan": (_i, [C.POINTER(PackJob), _i, _vp, C.POINTER(C.c_int)]),
+    "rsu_pack_run": (_i, [_vp, _i, _i, _vp]),
+    "rsu_first_layer_fold": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rsu_first_layer_grads": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "rsu_maxpool2x2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "rsu_skip_grad": (_i, [_vp, _i, _i, _i, _i, _vp, C.POINTER(View), _i, _i, _vp, _vp]),
     "rsu_relu_mask": (_i, [C.POINTER(View), C.POINTER(View), _vp, _vp]),

@@ -79,6 +79,63 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
     out[i] = __float2bfloat16(in[i]);
 }
 
+// All weight repacks of one optimizer step in ONE launch: every block looks its job up in a
+// device table (block ranges are prefix sums), then runs the same tile code as the kernels above.
+struct PackJobDev {
+  const float* in;
+  __nv_bfloat16* out;
+  int kind;  // 0 = transpose [T][R][C] -> [C][ld], 1 = permute [T][R][C] -> [R][T][C], 2 = cast
+  int T, R, C, ld;
+  int block_begin, block_count;
+};
+__global__ void pack_batch_kernel(const PackJobDev* __restrict__ jobs, int n_jobs) {
+  __shared__ float tile[32][33];
+  __shared__ int s_job;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int lo = 0, hi = n_jobs - 1;
+    const int b = blockIdx.x;
+    while (lo < hi) {  // last job whose block_begin <= b
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block_begin <= b) lo = mid;
+      else hi = mid - 1;
+    }
+    s_job = lo;
+  }
+  __syncthreads();
+  const PackJobDev j = jobs[s_job];
+  const int lb = blockIdx.x - j.block_begin;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (j.kind == 0) {
+    const int tiles_c = (j.C + 31) / 32, tiles_r = (j.R + 31) / 32;
+    const int t = lb / (tiles_c * tiles_r);
+    const int rem = lb % (tiles_c * tiles_r);
+    const int c0 = (rem % tiles_c) * 32, r0 = (rem / tiles_c) * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      if (r < j.R && c < j.C) tile[i][threadIdx.x] = j.in[(static_cast<long long>(t) * j.R + r) * j.C + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < j.R && c < j.C)
+        j.out[static_cast<long long>(c) * j.ld + t * j.R + r] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+  } else {
+    const long long total = 1LL * j.T * j.R * j.C;
+    for (long long i = lb * 256LL + tid; i < total; i += 256LL * j.block_count) {
+      if (j.kind == 2) {
+        j.out[i] = __float2bfloat16(j.in[i]);
+      } else {
+        const int c = static_cast<int>(i % j.C);
+        const long long tr = i / j.C;
+        const int r = static_cast<int>(tr % j.R);
+        const int t = static_cast<int>(tr / j.R);
+        j.out[(static_cast<long long>(r) * j.T + t) * j.C + c] = __float2bfloat16(j.in[i]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ first layer (Cin = 3)
 // color_space_adjust (unet.py:22-23) + dropout (unet.py:29-30) + 3x3 im2col into 64 channels.
 struct ColorW {
@@ -112,7 +169,10 @@ __global__ void color_im2col_kernel(const float* __restrict__ img, int N, int S,
     const int n = static_cast<int>(i / (1LL * Wo * Ho));
     float col[32];
 #pragma unroll
-    for (int j = 27; j < 32; ++j) col[j] = 0.f;
+    for (int j = 28; j < 32; ++j) col[j] = 0.f;
+    // constant-one column: the weight-gradient GEMM im2col^T dZ then carries BiasAddGrad in row 27
+    // (the packed forward weights are zero there, so the convolution itself is unaffected)
+    col[27] = 1.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int yy = y + oy + (t / 3) * d, xx = x + ox + (t % 3) * d;
@@ -188,6 +248,92 @@ __global__ void color_im2col_bwd_kernel(const float* __restrict__ img, int N, in
   __shared__ float red[12];
   if (threadIdx.x < 12) red[threadIdx.x] = 0.f;
   __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[j], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) atomicAdd(dw1 + threadIdx.x, red[threadIdx.x]);
+  else if (threadIdx.x < 12) atomicAdd(db1 + threadIdx.x - 9, red[threadIdx.x]);
+}
+
+// Folded first layer (Cin = 3, no dropout): color_space_adjust (unet.py:22-23) is linear and the
+// convolutions that follow are VALID, so
+//   conv(W, (x - 0.5) W1 + b1) + b  ==  conv(W', x - 0.5) + b'
+//   W'[tap, ci, co] = sum_c W1[ci, c] W[tap, c, co]      b'[co] = b[co] + sum_{tap, c} b1[c] W[tap, c, co]
+// The im2col buffer then holds the raw centred image and the backward pass needs neither the data
+// gradient of the convolution nor a pass over d(im2col): with Gx = im2col(x - 0.5)^T dZ (the
+// weight-gradient GEMM that is computed anyway) and db = column sums of dZ,
+//   dW[tap, c, co]  = sum_ci W1[ci, c] Gx[tap, ci, co] + b1[c] db[co]
+//   dW1[ci, c]      = sum_{tap, co} W[tap, c, co] Gx[tap, ci, co]
+//   db1[c]          = sum_{tap, co} W[tap, c, co] db[co]
+// One thread per output channel.
+__global__ void first_layer_fold_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                        int cout, __nv_bfloat16* __restrict__ wp,
+                                        float* __restrict__ bias_eff) {
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= cout) return;
+  float m1[9], c1[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m1[i] = __ldg(w1 + i);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c1[i] = __ldg(b1 + i);
+  float be = __ldg(b + co);
+  __nv_bfloat16* row = wp + static_cast<long long>(co) * 64;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float wt[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wt[c] = __ldg(w + (t * 3 + c) * cout + co);
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+      row[t * 3 + ci] =
+          __float2bfloat16(m1[ci * 3 + 0] * wt[0] + m1[ci * 3 + 1] * wt[1] + m1[ci * 3 + 2] * wt[2]);
+    be += c1[0] * wt[0] + c1[1] * wt[1] + c1[2] * wt[2];
+  }
+  for (int k = 27; k < 64; ++k) row[k] = __float2bfloat16(0.f);
+  bias_eff[co] = be;
+}
+
+__global__ void first_layer_grads_kernel(const float* __restrict__ gx, int ldg,
+                                         const float* __restrict__ w, const float* __restrict__ w1,
+                                         const float* __restrict__ b1, int cout,
+                                         float* __restrict__ dw, float* __restrict__ dbias,
+                                         float* __restrict__ dw1, float* __restrict__ db1) {
+  __shared__ float red[12];
+  if (threadIdx.x < 12) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+  float m1[9], c1[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m1[i] = __ldg(w1 + i);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c1[i] = __ldg(b1 + i);
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+    const float dbv = __ldg(gx + 27LL * ldg + co);
+    dbias[co] += dbv;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float g[3];
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) g[ci] = __ldg(gx + static_cast<long long>(t * 3 + ci) * ldg + co);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const long long wi = static_cast<long long>(t * 3 + c) * cout + co;
+        const float wv = __ldg(w + wi);
+        dw[wi] += m1[0 * 3 + c] * g[0] + m1[1 * 3 + c] * g[1] + m1[2 * 3 + c] * g[2] + c1[c] * dbv;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) acc[ci * 3 + c] += wv * g[ci];
+        acc[9 + c] += wv * dbv;
+      }
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
     float v = acc[j];
@@ -599,6 +745,69 @@ int rsu_color_im2col_bwd(const float* img, int N, int S, const void* dcol, int d
       img, N, S, static_cast<const __nv_bfloat16*>(dcol), dilation, oy, ox, Ho, Wo, dw1, db1, keep,
       seed);
   return check_launch("color_im2col_bwd");
+}
+
+int rsu_pack_plan(const rsu_pack_job* jobs_host, int n_jobs, void* table_dev, int* total_blocks) {
+  if (!jobs_host || n_jobs < 1 || n_jobs > 4096 || !table_dev || !total_blocks)
+    return set_error(RSU_EINVAL, "pack_plan: bad arguments");
+  PackJobDev* tab = new PackJobDev[n_jobs];
+  int blocks = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const rsu_pack_job& h = jobs_host[i];
+    if (h.kind < 0 || h.kind > 2 || h.T < 1 || h.R < 1 || h.C < 1) {
+      delete[] tab;
+      return set_error(RSU_EINVAL, "pack_plan: job %d invalid", i);
+    }
+    PackJobDev& d = tab[i];
+    d.in = h.in;
+    d.out = static_cast<__nv_bfloat16*>(h.out);
+    d.kind = h.kind;
+    d.T = h.T;
+    d.R = h.R;
+    d.C = h.C;
+    d.ld = h.ld > 0 ? h.ld : h.T * h.R;
+    d.block_begin = blocks;
+    if (h.kind == 0) {
+      d.block_count = h.T * ((h.R + 31) / 32) * ((h.C + 31) / 32);
+    } else {
+      const long long total = 1LL * h.T * h.R * h.C;
+      long long b = (total + 256 * 16 - 1) / (256 * 16);  // 16 elements per thread
+      d.block_count = static_cast<int>(b < 1 ? 1 : b);
+    }
+    blocks += d.block_count;
+  }
+  cudaError_t e = cudaMemcpy(table_dev, tab, sizeof(PackJobDev) * n_jobs, cudaMemcpyHostToDevice);
+  delete[] tab;
+  if (e != cudaSuccess) return set_error(RSU_ECUDA, "pack_plan: %s", cudaGetErrorString(e));
+  *total_blocks = blocks;
+  return RSU_OK;
+}
+
+int rsu_pack_plan_bytes(int n_jobs) { return static_cast<int>(sizeof(PackJobDev)) * n_jobs; }
+
+int rsu_pack_run(const void* table_dev, int n_jobs, int total_blocks, void* stream) {
+  if (!table_dev || n_jobs < 1 || total_blocks < 1) return set_error(RSU_EINVAL, "pack_run: bad arguments");
+  pack_batch_kernel<<<total_blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      static_cast<const PackJobDev*>(table_dev), n_jobs);
+  return check_launch("pack_batch");
+}
+
+int rsu_first_layer_fold(const float* w, const float* b, const float* w1, const float* b1, int cout,
+                         void* w_packed, float* bias_eff, void* stream) {
+  if (cout < 1) return set_error(RSU_EINVAL, "first_layer_fold: cout=%d", cout);
+  first_layer_fold_kernel<<<(cout + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
+      w, b, w1, b1, cout, static_cast<__nv_bfloat16*>(w_packed), bias_eff);
+  return check_launch("first_layer_fold");
+}
+
+int rsu_first_layer_grads(const float* gx, int ldg, const float* w, const float* w1, const float* b1,
+                          int cout, float* dw, float* dbias, float* dw1, float* db1, void* stream) {
+  if (cout < 1 || ldg < cout) return set_error(RSU_EINVAL, "first_layer_grads: cout=%d ldg=%d", cout, ldg);
+  int threads = ((cout + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  first_layer_grads_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(gx, ldg, w, w1, b1, cout, dw,
+                                                                    dbias, dw1, db1);
+  return check_launch("first_layer_grads");
 }
 
 int rsu_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, void* stream) {

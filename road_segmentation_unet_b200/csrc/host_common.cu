@@ -98,13 +98,14 @@ int encode_weight_map(CUtensorMap* map, const void* ptr, int K, int N, int box_n
   return RSU_OK;
 }
 
-void pick_tile(int W, int H, int max_tw, int max_th, bool mult16, int* TW, int* TH) {
+void pick_tile(int W, int H, int max_tw, int max_th, bool mult16, int* TW, int* TH, int max_pixels) {
   long best_tiles = -1;
   int bw = 0, bh = 0;
-  if (max_tw > 128) max_tw = 128;
+  if (max_pixels > 128 || max_pixels < 1) max_pixels = 128;
+  if (max_tw > max_pixels) max_tw = max_pixels;
   for (int tw = max_tw; tw >= 1; --tw) {
     if (tw < 8 && max_tw >= 8) break;  // keep contiguous runs >= 1 KiB when possible
-    int th_max = 128 / tw;
+    int th_max = max_pixels / tw;
     if (th_max > max_th) th_max = max_th;
     for (int th = th_max; th >= 1; --th) {
       if (mult16 && (tw * th) % 16 != 0) continue;
@@ -119,6 +120,27 @@ void pick_tile(int W, int H, int max_tw, int max_th, bool mult16, int* TW, int* 
   }
   *TW = bw;  // 0 x 0 when no admissible tile exists
   *TH = bh;
+}
+
+int choose_ksplit(int mn_units, int k_tiles, int sms, double tile_cost, double unit_cost,
+                  int min_tiles) {
+  if (min_tiles < 1) min_tiles = 1;
+  int kmax = k_tiles / min_tiles;
+  if (kmax < 1) kmax = 1;
+  if (kmax > 8192) kmax = 8192;
+  int best = 1;
+  double best_cost = -1.0;
+  for (int k = 1; k <= kmax; ++k) {
+    const long long units = 1LL * k * mn_units;
+    const long long waves = (units + sms - 1) / sms;
+    const double per_unit = static_cast<double>((k_tiles + k - 1) / k) * tile_cost + unit_cost;
+    const double cost = static_cast<double>(waves) * per_unit;
+    if (best_cost < 0.0 || cost < best_cost * (1.0 - 1e-9)) {
+      best_cost = cost;
+      best = k;
+    }
+  }
+  return best;
 }
 
 }  // namespace rsu

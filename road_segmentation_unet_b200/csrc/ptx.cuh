@@ -259,6 +259,14 @@ __device__ __forceinline__ void load_mask_bits4(const __nv_bfloat16* px, int n_c
   }
 }
 
+// fp32 x 4 reduction into global memory without a return value (REDG.E.ADD.F32x4): the split-K
+// epilogues of the weight-gradient kernels; addr must be 16-byte aligned.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

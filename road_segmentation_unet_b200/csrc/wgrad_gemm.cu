@@ -17,10 +17,11 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace rsu {
 
 constexpr int kWgThreads = 256;
-constexpr int kBoxBytes = 16384;  // one 64-channel atom: up to 128 pixel rows of 128 B
 constexpr int kWgTmemCols = 512;
 constexpr int kWgAccStride = 256;
 
@@ -45,14 +46,14 @@ __device__ __forceinline__ AtomCoord decode_atom(const WgradParams& p, int atom,
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-    wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int stages) {
+    wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int stages, uint32_t atom_bytes) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int n_b_atoms = p.BN / 64;
-  const uint32_t stage_bytes = static_cast<uint32_t>(2 + n_b_atoms) * kBoxBytes;
+  const uint32_t stage_bytes = static_cast<uint32_t>(2 + n_b_atoms) * atom_bytes;
   const uint32_t bar_base = smem_base + stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
@@ -128,10 +129,10 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           mbar_expect_tx(fb, tx_bytes);
           tma_load_4d(dst, &p.a_map[a0.src], fb, a0.chunk * 64, x0 + a0.dx, y0 + a0.dy, img);
           if (n_a == 2)
-            tma_load_4d(dst + kBoxBytes, &p.a_map[a1.src], fb, a1.chunk * 64, x0 + a1.dx, y0 + a1.dy,
+            tma_load_4d(dst + atom_bytes, &p.a_map[a1.src], fb, a1.chunk * 64, x0 + a1.dx, y0 + a1.dy,
                         img);
           for (int j = 0; j < n_b_atoms; ++j)
-            tma_load_4d(dst + (2 + j) * kBoxBytes, &p.b_map, fb, n0 + j * 64, x0 + p.b_off_x,
+            tma_load_4d(dst + (2 + j) * atom_bytes, &p.b_map, fb, n0 + j * 64, x0 + p.b_off_x,
                         y0 + p.b_off_y, img);
         }
         __syncwarp();
@@ -167,8 +168,8 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint32_t a_lo = desc_lo_sw128(a_addr, kBoxBytes);
-          const uint32_t b_lo = desc_lo_sw128(a_addr + 2 * kBoxBytes, kBoxBytes);
+          const uint32_t a_lo = desc_lo_sw128(a_addr, atom_bytes);
+          const uint32_t b_lo = desc_lo_sw128(a_addr + 2 * atom_bytes, atom_bytes);
           const uint32_t first = pt != pt0 ? 1u : 0u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -210,7 +211,9 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(orow + ch * 32 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(orow + ch * 32 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         }
       }
       tc_fence_before();
@@ -225,6 +228,16 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 }
 
 int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_done);  // wgrad_halo.cu
+
+// pixels per K step of the per-tap kernel (RSU_WGRAD_TILE = 64 | 128 overrides, for A/B runs)
+static int wgrad_tile_pixels() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("RSU_WGRAD_TILE");
+    v = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  return v;
+}
 
 }  // namespace rsu
 
@@ -269,8 +282,11 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
     if (d->src[s].H < max_th) max_th = d->src[s].H;
     chunks_total += d->src[s].C / 64;
   }
+  // 64-pixel K steps: a stage is (2 + BN/64) x 8 KiB, so four stages fit even at BN = 256 (with
+  // 128-pixel steps only two 96 KiB stages did, and the tensor pipe idled ~45 % of the time
+  // waiting for loads -- profiles/r1_step_metrics.txt)
   int TW, TH;
-  pick_tile(d->W, d->H, max_tw, max_th, true, &TW, &TH);
+  pick_tile(d->W, d->H, max_tw, max_th, true, &TW, &TH, wgrad_tile_pixels());
   if (TW < 1 || TH < 1 || (TW * TH) % 16 != 0)
     return set_error(RSU_EINVAL, "no valid pixel tile for %dx%d (need TW*TH %% 16 == 0)", d->W, d->H);
   p.TW = TW;
@@ -307,14 +323,15 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
 
   const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
   const int mn_units = p.n_tiles_m * p.n_tiles_n;
-  int ksplit = (2 * num_sms() + mn_units - 1) / mn_units;
-  if (ksplit > pix_tiles) ksplit = pix_tiles;
-  if (ksplit < 1) ksplit = 1;
-  p.ksplit = ksplit;
+  // cycles: one K step = (pixels / 16) MMAs of BN / 2 cycles; a unit ends with a BN-column
+  // epilogue of fp32 reductions that overlaps the next unit only partly
+  p.ksplit = choose_ksplit(mn_units, pix_tiles, num_sms(), (TW * TH / 16) * (p.BN / 2.0),
+                           1500.0 + 12.0 * p.BN, 4);
 
-  const int stage_bytes = (2 + p.BN / 64) * kBoxBytes;
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > 6) stages = 6;
+  const int atom_bytes = ((TW * TH * 128) + 1023) & ~1023;
+  const int stage_bytes = (2 + p.BN / 64) * atom_bytes;
+  int stages = (220 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   const int smem = 1024 + stages * stage_bytes + 8 * (2 * stages + 4) + 16;
   static bool attr_set = false;
@@ -323,9 +340,9 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const long long total = 1LL * mn_units * ksplit;
+  const long long total = 1LL * mn_units * p.ksplit;
   int grid = num_sms();
   if (total < grid) grid = static_cast<int>(total);
-  wgrad_gemm_kernel<<<grid, kWgThreads, smem, stream>>>(p, stages);
+  wgrad_gemm_kernel<<<grid, kWgThreads, smem, stream>>>(p, stages, static_cast<uint32_t>(atom_bytes));
   return check_launch("wgrad_gemm_kernel");
 }

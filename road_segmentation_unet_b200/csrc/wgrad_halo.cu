@@ -240,7 +240,9 @@ __global__ void __launch_bounds__(kWhThreads, 1)
           tmem_ld_wait();
           if (is_w || is_b) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(orow + ch * 32 + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(orow + ch * 32 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           }
         }
       }
@@ -309,10 +311,10 @@ int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_do
   const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
   const int mn_units = p.chunks_total * p.n_tiles_n;
   const int sms = num_sms();
-  int ksplit = (4 * sms + mn_units - 1) / mn_units;
-  if (ksplit > pix_tiles / 16) ksplit = pix_tiles / 16;
-  if (ksplit < 1) ksplit = 1;
-  p.ksplit = ksplit;
+  // cycles per 128-pixel tile: 8 K steps x ceil(taps / 2) MMAs of 128 x 64 x 16 (48 cycles each,
+  // shared-memory operand bandwidth bound); the single accumulator set is drained by fp32
+  // reductions before the next unit may start
+  p.ksplit = choose_ksplit(mn_units, pix_tiles, sms, 8.0 * ((d->n_taps + 1) / 2) * 48.0, 6000.0, 8);
 
   const int stage_bytes = static_cast<int>(p.a_stage_bytes) + kWhBBytes;
   int stages = (227 * 1024 - 1024 - kOnesBytes - 512) / stage_bytes;
@@ -326,7 +328,7 @@ int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_do
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const long long total = 1LL * mn_units * ksplit;
+  const long long total = 1LL * mn_units * p.ksplit;
   int grid = total < sms ? static_cast<int>(total) : sms;
   wgrad_halo_kernel<<<grid, kWhThreads, smem, stream>>>(p);
   *bias_done = p.bias_grad != nullptr ? 1 : 0;

@@ -144,6 +144,29 @@ def cast_bf16(src, out):
     call("rsu_cast_bf16", _ptr(src), _ptr(out), src.numel())
 
 
+PACK_TRANSPOSE, PACK_PERMUTE, PACK_CAST = 0, 1, 2
+
+
+class PackPlan:
+    """A fixed list of weight repacks (fp32 master -> bf16 operand layouts) run as one launch.
+    jobs: [(kind, fp32 source tensor, bf16 destination tensor, T, R, C, ld)]."""
+
+    def __init__(self, jobs, device):
+        lib = _lib.load()
+        n = len(jobs)
+        arr = (_lib.PackJob * n)()
+        for i, (kind, src, dst, T, R, Cc, ld) in enumerate(jobs):
+            arr[i] = _lib.PackJob(src.data_ptr(), dst.data_ptr(), kind, T, R, Cc, ld)
+        self._keep = [(src, dst) for (_, src, dst, _, _, _, _) in jobs]  # keep buffers alive
+        self.table = torch.empty(lib.rsu_pack_plan_bytes(n), dtype=torch.uint8, device=device)
+        blocks = C.c_int(0)
+        _lib.check(lib.rsu_pack_plan(arr, n, C.c_void_p(self.table.data_ptr()), C.byref(blocks)))
+        self.n, self.blocks = n, blocks.value
+
+    def run(self):
+        call("rsu_pack_run", _ptr(self.table), self.n, self.blocks)
+
+
 # ------------------------------------------------------------------ conv 3x3 (unet.py:34-45,88-91)
 def conv3x3_fwd(srcs, w_fwd, bias, out, dilation=1, relu=True, algo=ALGO_AUTO):
     """srcs: [(tensor, off_y, off_x)] in concat order; out [N,Ho,Wo,Cout] bf16."""
@@ -249,6 +272,19 @@ def color_im2col_bwd(img, dcol, dilation, oy, ox, dw1, db1, keep=1.0, seed=0):
     n, s = img.shape[0], img.shape[1]
     call("rsu_color_im2col_bwd", _ptr(img), n, s, _ptr(dcol), dilation, oy, ox, dcol.shape[1],
          dcol.shape[2], _ptr(dw1), _ptr(db1), float(keep), int(seed))
+
+
+def first_layer_fold(w, b, w1, b1, w_packed, bias_eff):
+    """Fold color_space_adjust into a Cin = 3 convolution (w: HWIO fp32 [3,3,3,cout])."""
+    call("rsu_first_layer_fold", _ptr(w), _ptr(b), _ptr(w1), _ptr(b1), w.shape[3], _ptr(w_packed),
+         _ptr(bias_eff))
+
+
+def first_layer_grads(gx, w, w1, b1, dw, dbias, dw1, db1):
+    """Gradients of the folded first layer from gx = im2col(x - 0.5)^T dZ (fp32 [rows, cout];
+    row 27 = BiasAddGrad through the constant-one im2col column)."""
+    call("rsu_first_layer_grads", _ptr(gx), gx.stride(0), _ptr(w), _ptr(w1), _ptr(b1),
+         w.shape[3], _ptr(dw), _ptr(dbias), _ptr(dw1), _ptr(db1))
 
 
 def launch_count():

@@ -264,13 +264,16 @@ class UNet:
         # first layer im2col buffers (Cin = 3 -> 64 padded channels)
         s0 = self.in_size[0]
         self.col = self._bf(B, s0 - 2, s0 - 2, 64)
-        self.dcol = self._bf(B, s0 - 2, s0 - 2, 64) if tr else None
+        self.dcol = None  # gradient of the im2col matrix: only the dropout path needs it (lazy)
         if self.dilated and L > 1:
             t0 = self.up_size[L - 2]
             self.colD = self._bf(B, t0 + 4, t0 + 4, 64)
-            self.dcolD = self._bf(B, t0 + 4, t0 + 4, 64) if tr else None
         else:
-            self.colD = self.dcolD = None
+            self.colD = None
+        self.dcolD = None
+        # identity colour transform: the folded first layer (keep == 1) feeds im2col(x - 0.5)
+        self._eye3 = torch.eye(3, dtype=torch.float32, device=self.device)
+        self._zero3 = torch.zeros(3, dtype=torch.float32, device=self.device)
         self.U, self.C1, self.C2 = [], [], []
         self.dCat, self.dC1, self.dC2 = [], [], []
         for j in range(L - 1):
@@ -309,6 +312,9 @@ class UNet:
                     c.w_fwd = torch.zeros(cout, 64, dtype=torch.bfloat16, device=dev)
                     c.w_dgrad = torch.zeros(64, cout, dtype=torch.bfloat16, device=dev) if tr else None
                     c.dw_stage = torch.zeros(64, cout, dtype=torch.float32, device=dev) if tr else None
+                    # color_space_adjust folded into the kernel / bias (used when keep == 1)
+                    c.w_fold = torch.zeros(cout, 64, dtype=torch.bfloat16, device=dev)
+                    c.bias_fold = torch.zeros(cout, dtype=torch.float32, device=dev)
                 else:
                     c.w_fwd = self._bf(cout, 9 * cin)
                     c.w_dgrad = self._bf(cin, 9 * cout) if tr else None
@@ -318,22 +324,35 @@ class UNet:
                 self.convs.pop("conv_dilut_%d/atrous_conv%d" % (L - 1, k), None)
 
     # ------------------------------------------------------------------ weights
-    def pack_weights(self):
-        """fp32 master (TensorFlow layouts) -> bf16 GEMM operand layouts; run after every update."""
+    def _pack_jobs(self):
+        jobs = []
         for key, c in self.convs.items():
             w = self.var(key + "/kernel")
             if key.startswith("up_conv"):
-                ops.cast_bf16(w, c.w_fwd)
+                jobs.append((ops.PACK_CAST, w, c.w_fwd, 1, 1, w.numel(), 0))
                 if c.w_dgrad is not None:
-                    ops.pack_conv_fwd(w, c.w_dgrad, 1, 4 * c.cout, c.cin)
+                    jobs.append((ops.PACK_TRANSPOSE, w, c.w_dgrad, 1, 4 * c.cout, c.cin, 0))
             elif c.cin == 3:
-                ops.pack_conv_fwd(w, c.w_fwd, 1, 27, c.cout, ld=64)
+                jobs.append((ops.PACK_TRANSPOSE, w, c.w_fwd, 1, 27, c.cout, 64))
                 if c.w_dgrad is not None:
-                    ops.pack_conv_dgrad(w, c.w_dgrad, 1, 27, c.cout)
+                    jobs.append((ops.PACK_PERMUTE, w, c.w_dgrad, 1, 27, c.cout, 0))
             else:
-                ops.pack_conv_fwd(w, c.w_fwd, 9, c.cin, c.cout)
+                jobs.append((ops.PACK_TRANSPOSE, w, c.w_fwd, 9, c.cin, c.cout, 0))
                 if c.w_dgrad is not None:
-                    ops.pack_conv_dgrad(w, c.w_dgrad, 9, c.cin, c.cout)
+                    jobs.append((ops.PACK_PERMUTE, w, c.w_dgrad, 9, c.cin, c.cout, 0))
+        return jobs
+
+    def pack_weights(self):
+        """fp32 master (TensorFlow layouts) -> bf16 GEMM operand layouts; run after every update:
+        one table-driven launch for all repacks plus the two folded first-layer kernels."""
+        if getattr(self, "_pack_plan", None) is None:
+            self._pack_plan = ops.PackPlan(self._pack_jobs(), self.device)
+        self._pack_plan.run()
+        for key, c in self.convs.items():
+            if c.cin == 3 and not key.startswith("up_conv"):
+                ops.first_layer_fold(self.var(key + "/kernel"), self.var(key + "/bias"),
+                                     self.var("color_space_adjust/kernel"),
+                                     self.var("color_space_adjust/bias"), c.w_fold, c.bias_fold)
 
     # ------------------------------------------------------------------ forward
     def _site_seed(self, site):
@@ -357,17 +376,22 @@ class UNet:
             dil_live = self.dilated and i < L - 1
             o2 = self.dil_off[i]
             if i == 0:
+                # without dropout color_space_adjust is folded into the convolution: the im2col
+                # matrix holds x - 0.5 (identity transform) and the kernel / bias are W1.W, b + b1.W
                 seed0 = self._site_seed(site)
-                ops.color_im2col(images, w1, b1, 1, 0, 0, self.col, keep, seed0)
+                cw, cb = (w1, b1) if drop else (self._eye3, self._zero3)
+                ops.color_im2col(images, cw, cb, 1, 0, 0, self.col, keep, seed0)
                 self._tag(reg1.name)
-                ops.conv_gemm([(self.col, 0, 0)], [(0, 0)], reg1.w_fwd, self.A1[0], f[0],
-                              bias=bias(reg1.name), relu=True)
+                ops.conv_gemm([(self.col, 0, 0)], [(0, 0)], reg1.w_fwd if drop else reg1.w_fold,
+                              self.A1[0], f[0], bias=bias(reg1.name) if drop else reg1.bias_fold,
+                              relu=True)
                 if dil_live:
                     d1 = self.convs["conv_dilut_0/atrous_conv1"]
-                    ops.color_im2col(images, w1, b1, 2, o2, o2, self.colD, keep, seed0)
+                    ops.color_im2col(images, cw, cb, 2, o2, o2, self.colD, keep, seed0)
                     self._tag(d1.name)
-                    ops.conv_gemm([(self.colD, 0, 0)], [(0, 0)], d1.w_fwd, self.D1[0], f[0],
-                                  bias=bias(d1.name), relu=True)
+                    ops.conv_gemm([(self.colD, 0, 0)], [(0, 0)], d1.w_fwd if drop else d1.w_fold,
+                                  self.D1[0], f[0], bias=bias(d1.name) if drop else d1.bias_fold,
+                                  relu=True)
             else:
                 src = self.Pool[i - 1]
                 if drop:
@@ -447,14 +471,26 @@ class UNet:
             ops.conv3x3_dgrad(dz, conv.w_dgrad, dx, dilation=conv.dilation, mask=mask,
                               accumulate=accumulate)
 
-    def _first_bwd(self, conv, col, dcol, dz, dilation, oy, ox):
+    def _first_bwd(self, conv, col, which_dcol, dz, dilation, oy, ox):
         """Cin = 3 convolution through its im2col matrix, plus d(color_space_adjust)."""
         self._tag(conv.name)
         g = lambda n: self.var(conv.name + "/" + n, "grads")
         conv.dw_stage.zero_()
         ops.wgrad_gemm([(col, 0, 0)], [(0, 0)], dz, (0, 0), conv.dw_stage, (dz.shape[1], dz.shape[2]))
+        if self._keep >= 1.0:
+            # folded layer: everything follows from the 28 x Cout matrix im2col(x - 0.5)^T dZ
+            # (row 27, the constant-one column, is the bias gradient)
+            ops.first_layer_grads(conv.dw_stage, self.var(conv.name + "/kernel"),
+                                  self.var("color_space_adjust/kernel"),
+                                  self.var("color_space_adjust/bias"), g("kernel"), g("bias"),
+                                  self.var("color_space_adjust/kernel", "grads"),
+                                  self.var("color_space_adjust/bias", "grads"))
+            return
         g("kernel").view(27, conv.cout).add_(conv.dw_stage[:27])
-        ops.bias_grad(dz, g("bias"))
+        g("bias").add_(conv.dw_stage[27])
+        if getattr(self, which_dcol) is None:
+            setattr(self, which_dcol, torch.empty_like(col))
+        dcol = getattr(self, which_dcol)
         ops.conv_gemm([(dz, 0, 0)], [(0, 0)], conv.w_dgrad, dcol, 64)
         ops.color_im2col_bwd(self._images, dcol, dilation, oy, ox,
                              self.var("color_space_adjust/kernel", "grads"),
@@ -516,7 +552,7 @@ class UNet:
                 src = self._drop_pool[i] if drop else self.Pool[i - 1]
                 self._conv_bwd(reg1, [(src, 0, 0)], self.dA1[i], self.dIn[i])
             else:
-                self._first_bwd(reg1, self.col, self.dcol, self.dA1[0], 1, 0, 0)
+                self._first_bwd(reg1, self.col, "dcol", self.dA1[0], 1, 0, 0)
             if dil_live:
                 d1 = self.convs["conv_dilut_%d/atrous_conv1" % i]
                 d2 = self.convs["conv_dilut_%d/atrous_conv2" % i]
@@ -528,7 +564,7 @@ class UNet:
                     win = self.dIn[i][:, o2:o2 + tt, o2:o2 + tt, :]
                     self._conv_bwd(d1, [(src, o2, o2)], self.dD1[i], win, accumulate=True)
                 else:
-                    self._first_bwd(d1, self.colD, self.dcolD, self.dD1[0], 2, o2, o2)
+                    self._first_bwd(d1, self.colD, "dcolD", self.dD1[0], 2, o2, o2)
             self._ready(enc_buckets[i])
 
     # ------------------------------------------------------------------ optimizer

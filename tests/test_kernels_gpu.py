@@ -303,8 +303,9 @@ def test_color_im2col(ops, case):
     out = torch.full((n, ho, wo, 64), 3.0, dtype=torch.bfloat16, device="cuda")
     d_img = dev(img, torch.float32)
     ops.color_im2col(d_img, dev(w1, torch.float32), dev(b1, torch.float32), d, oy, ox, out, keep, seed)
+    col[..., 27] = 1.0  # constant-one column (BiasAddGrad through the weight-gradient GEMM)
     assert rel_err(out.float().cpu().numpy(), bf(col)) < 1e-6 + 4e-3
-    assert np.abs(out.float().cpu().numpy()[..., 27:]).max() == 0
+    assert np.abs(out.float().cpu().numpy()[..., 28:]).max() == 0
     # backward: dW1, db1 from d(col)
     dcol = bf(rs.randn(n, ho, wo, 64).astype(np.float32))
     dnet = np.zeros((n, s, s, 3), dtype=np.float64)
@@ -339,6 +340,58 @@ def test_first_layer_via_im2col(ops):
     ops.conv_gemm([(col, 0, 0)], [(0, 0)], wp, out, cout, bias=dev(b, torch.float32), relu=True)
     ref = torch.relu(O.conv2d_valid(torch.tensor(bf(img - 0.5)), torch.tensor(w), torch.tensor(b))).numpy()
     assert rel_err(out.float().cpu().numpy(), ref) < 6e-3
+
+
+def test_first_layer_fold_and_grads(ops):
+    """color_space_adjust folded into the Cin = 3 convolution (keep == 1): forward through the
+    folded kernel / bias equals conv(W, (x-0.5) W1 + b1) + b, and the gradients of W, W1, b1
+    recovered from Gx = im2col(x-0.5)^T dZ equal autograd through the unfolded graph."""
+    rs = np.random.RandomState(13)
+    n, s, cout = 2, 22, 64
+    img = rs.rand(n, s, s, 3).astype(np.float32)
+    w1 = (np.eye(3) + 0.3 * rs.randn(3, 3)).astype(np.float32)
+    b1 = (0.2 * rs.randn(3)).astype(np.float32)
+    w = (rs.randn(3, 3, 3, cout) / np.sqrt(27)).astype(np.float32)
+    b = rs.randn(cout).astype(np.float32)
+    ho = s - 2
+    d_w, d_b = dev(w, torch.float32), dev(b, torch.float32)
+    d_w1, d_b1 = dev(w1, torch.float32), dev(b1, torch.float32)
+    wp = torch.full((cout, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    be = torch.zeros(cout, dtype=torch.float32, device="cuda")
+    ops.first_layer_fold(d_w, d_b, d_w1, d_b1, wp, be)
+    w_fold = np.einsum("ic,tcn->tin", w1.astype(np.float64), w.reshape(9, 3, cout).astype(np.float64))
+    assert rel_err(wp.float().cpu().numpy()[:, :27], bf(w_fold.reshape(27, cout).T.astype(np.float32))) < 1e-6
+    assert np.abs(wp.float().cpu().numpy()[:, 27:]).max() == 0
+    ref_be = b + np.einsum("c,tcn->n", b1.astype(np.float64), w.reshape(9, 3, cout).astype(np.float64))
+    assert rel_err(be.cpu().numpy(), ref_be) < 1e-5
+    # forward through the folded operands
+    col = torch.zeros(n, ho, ho, 64, dtype=torch.bfloat16, device="cuda")
+    eye, zero = torch.eye(3, device="cuda"), torch.zeros(3, device="cuda")
+    ops.color_im2col(dev(img, torch.float32), eye, zero, 1, 0, 0, col)
+    out = torch.zeros(n, ho, ho, cout, dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([(col, 0, 0)], [(0, 0)], wp, out, cout, bias=be, relu=False)
+    xt = torch.tensor(img, dtype=torch.float64)
+    tw = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    tw1 = torch.tensor(w1, dtype=torch.float64, requires_grad=True)
+    tb1 = torch.tensor(b1, dtype=torch.float64, requires_grad=True)
+    net0 = (xt - 0.5) @ tw1 + tb1
+    y = O.conv2d_valid(net0, tw, torch.tensor(b, dtype=torch.float64))
+    assert rel_err(out.float().cpu().numpy(), y.detach().numpy()) < 1e-2
+    # backward from a given dZ
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    y.backward(torch.tensor(dz, dtype=torch.float64))
+    gx = torch.zeros(64, cout, dtype=torch.float32, device="cuda")
+    d_dz = dev(dz)
+    ops.wgrad_gemm([(col, 0, 0)], [(0, 0)], d_dz, (0, 0), gx, (ho, ho))
+    db = torch.zeros(cout, dtype=torch.float32, device="cuda")
+    dw = torch.zeros(3, 3, 3, cout, dtype=torch.float32, device="cuda")
+    dw1 = torch.zeros(3, 3, dtype=torch.float32, device="cuda")
+    db1 = torch.zeros(3, dtype=torch.float32, device="cuda")
+    ops.first_layer_grads(gx, d_w, d_w1, d_b1, dw, db, dw1, db1)
+    assert rel_err(db.cpu().numpy(), dz.astype(np.float64).sum(axis=(0, 1, 2))) < 1e-4
+    assert rel_err(dw.cpu().numpy(), tw.grad.numpy()) < 1e-2
+    assert rel_err(dw1.cpu().numpy(), tw1.grad.numpy()) < 1e-2
+    assert rel_err(db1.cpu().numpy(), tb1.grad.numpy()) < 1e-2
 
 
 # ------------------------------------------------------------------ halo-tile kernels (algo = 2)

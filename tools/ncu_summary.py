@@ -35,6 +35,9 @@ def main():
         a[0] += v
         a[1] += 1
         total += v
+    if "--count" in sys.argv:
+        print(sum(a[1] for a in agg.values()))
+        return
     print("total %.3f ms over %d launches" % (total / 1e6, sum(a[1] for a in agg.values())))
     print("%-60s %10s %7s %8s %10s" % ("kernel", "ms", "share", "launches", "avg us"))
     for name, (ns, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:

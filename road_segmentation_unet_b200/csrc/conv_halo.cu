@@ -64,6 +64,127 @@ struct ConvHaloParams {
   CUtensorMap mask_map;  // same geometry over the mask tensor
 };
 
+struct HaloIssueCtx {
+  uint32_t smem_base, b_base, bar_base, tmem_base;
+  int u_begin, u_step, u_end, chunks_total;
+};
+
+// The MMA-issuing warp of conv_halo_kernel.  NT / MT / BN are compile-time for the shapes the
+// network uses (0 = read them from the parameter block): with runtime tap counts the unrolled
+// loop re-read its bounds from constant memory and branched before every group of four
+// tcgen05.mma, and the issuing thread -- not shared memory or the tensor pipe -- set the pace
+// (ncu source view: the warp never waited on a full barrier).  Descriptors are (lo, hi) words:
+// hi (stride, version, swizzle) is constant, lo = start address >> 4 advances by the tap window
+// offset / 16-row block / 32-byte K step.
+template <int NT_, int MT_, int BN_>
+__device__ __forceinline__ void halo_mma_issuer(const ConvHaloParams& p, const HaloIssueCtx& c) {
+  const int NT = NT_ ? NT_ : p.n_taps;
+  const int MT = MT_ ? MT_ : p.MT;
+  const uint32_t bn = BN_ ? static_cast<uint32_t>(BN_) : static_cast<uint32_t>(p.BN);
+  const int SA = p.stages_a, SB = p.stages_b;
+  const uint32_t bar_base = c.bar_base;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+
+  const uint32_t idesc = make_idesc_bf16(kBlockM, static_cast<int>(bn), false, false);
+  const uint32_t a_hi = desc_hi_sw128(static_cast<uint32_t>(p.Wh) * 128u);
+  const uint32_t b_hi = desc_hi_sw128(1024u);
+  uint32_t tap_off[kMaxTaps];
+#pragma unroll
+  for (int t = 0; t < kMaxTaps; ++t) tap_off[t] = t < NT ? static_cast<uint32_t>(p.tap_row[t]) * 8u : 0u;
+  const uint32_t mt_off = static_cast<uint32_t>(kHaloTH * p.Wh) * 8u;
+  const uint32_t b_stage_bytes = bn * 128u;
+  const uint32_t b_step = b_stage_bytes >> 4;
+  const uint32_t acc_set_cols = static_cast<uint32_t>(MT) * bn;
+  const uint32_t a_stage16 = p.a_stage_bytes >> 4;
+  const uint32_t a_lo_base = desc_lo_sw128(c.smem_base, 16);
+  const uint32_t b_lo_base = desc_lo_sw128(c.b_base, 16);
+  const bool resident = p.resident != 0;
+  uint32_t sa = 0, sb = 0, pa = 0, pb = 0;
+  uint32_t a_lo = a_lo_base, b_lo_s = b_lo_base;  // descriptors of stage sa / sb
+  uint32_t acc_it = 0;
+  bool first = true;
+  for (int u = c.u_begin; u < c.u_end; u += c.u_step, ++acc_it) {
+    const uint32_t acc = acc_it & 1u;
+    const uint32_t acc_phase = (acc_it >> 1) & 1u;
+    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    tc_fence_after();
+    const uint32_t d_tmem = c.tmem_base + acc * acc_set_cols;
+    uint32_t b_lo_c = b_lo_base;  // resident weights: descriptor of chunk cg, tap 0
+    for (int cg = 0; cg < c.chunks_total; ++cg) {
+      mbar_wait(a_full(sa), pa);
+      if (resident) {
+        // weights of this chunk live in stages [cg * NT, (cg + 1) * NT)
+        if (first) {
+          for (int t = 0; t < NT; ++t) mbar_wait(b_full(cg * NT + t), 0);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int t = 0; t < kMaxTaps; ++t) {
+            if (t < NT) {
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                if (mt < MT) {
+#pragma unroll
+                  for (int j = 0; j < kBlockK / 16; ++j)
+                    umma_bf16_lohi(d_tmem + mt * bn, a_lo + tap_off[t] + mt * mt_off + 2u * j, a_hi,
+                                   b_lo_c + t * b_step + 2u * j, b_hi, idesc,
+                                   (t | j) != 0 ? 1u : (cg != 0 ? 1u : 0u));
+                }
+              }
+            }
+          }
+          umma_commit(a_empty(sa));
+        }
+        __syncwarp();
+        b_lo_c += static_cast<uint32_t>(NT) * b_step;
+      } else {
+#pragma unroll
+        for (int t = 0; t < kMaxTaps; ++t) {
+          if (t < NT) {
+            mbar_wait(b_full(sb), pb);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                if (mt < MT) {
+#pragma unroll
+                  for (int j = 0; j < kBlockK / 16; ++j)
+                    umma_bf16_lohi(d_tmem + mt * bn, a_lo + tap_off[t] + mt * mt_off + 2u * j, a_hi,
+                                   b_lo_s + 2u * j, b_hi, idesc, (t | j) != 0 ? 1u : (cg != 0 ? 1u : 0u));
+                }
+              }
+              umma_commit(b_empty(sb));
+              if (t == NT - 1) umma_commit(a_empty(sa));
+            }
+            __syncwarp();
+            b_lo_s += b_step;
+            if (++sb == static_cast<uint32_t>(SB)) {
+              sb = 0;
+              pb ^= 1u;
+              b_lo_s = b_lo_base;
+            }
+          }
+        }
+      }
+      a_lo += a_stage16;
+      if (++sa == static_cast<uint32_t>(SA)) {
+        sa = 0;
+        pa ^= 1u;
+        a_lo = a_lo_base;
+      }
+    }
+    if (elect_one()) umma_commit(tfull_bar(acc));
+    __syncwarp();
+    first = false;
+  }
+}
+
 __global__ void __launch_bounds__(kHaloThreads, 1)
     conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -203,91 +324,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    // Descriptors as (lo, hi) words: hi (stride, version, swizzle) is constant, lo = start
-    // address >> 4 advances by the tap window offset / 16-row block / 32-byte K step.
-    const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, false, false);
-    const uint32_t a_hi = desc_hi_sw128(static_cast<uint32_t>(p.Wh) * 128u);
-    const uint32_t b_hi = desc_hi_sw128(1024u);
-    uint32_t tap_off[kMaxTaps];
-#pragma unroll
-    for (int t = 0; t < kMaxTaps; ++t) tap_off[t] = t < p.n_taps ? static_cast<uint32_t>(p.tap_row[t]) * 8u : 0u;
-    const uint32_t mt_off = static_cast<uint32_t>(kHaloTH * p.Wh) * 8u;
-    const uint32_t b_step = b_stage_bytes >> 4;
-    const uint32_t bn = static_cast<uint32_t>(p.BN);
-    uint32_t sa = 0, sb = 0, pa = 0, pb = 0;
-    uint32_t acc_it = 0;
-    bool first = true;
-    for (int u = u_begin; u < u_end; u += u_step, ++acc_it) {
-      const uint32_t acc = acc_it & 1u;
-      const uint32_t acc_phase = (acc_it >> 1) & 1u;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * acc_set_cols;
-      for (int cg = 0; cg < chunks_total; ++cg) {
-        mbar_wait(a_full(sa), pa);
-        const uint32_t a_lo = desc_lo_sw128(smem_base + sa * p.a_stage_bytes, 16);
-        if (p.resident) {
-          // weights of this chunk live in stages [cg * n_taps, (cg + 1) * n_taps)
-          if (first) {
-            for (int t = 0; t < p.n_taps; ++t) mbar_wait(b_full(cg * p.n_taps + t), 0);
-          }
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t b_lo0 = desc_lo_sw128(b_base + cg * p.n_taps * b_stage_bytes, 16);
-#pragma unroll
-            for (int t = 0; t < kMaxTaps; ++t) {
-              if (t < p.n_taps) {
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                  if (mt < p.MT) {
-#pragma unroll
-                    for (int j = 0; j < kBlockK / 16; ++j)
-                      umma_bf16_lohi(d_tmem + mt * bn, a_lo + tap_off[t] + mt * mt_off + 2u * j, a_hi,
-                                     b_lo0 + t * b_step + 2u * j, b_hi, idesc,
-                                     (cg | t | j) != 0 ? 1u : 0u);
-                  }
-                }
-              }
-            }
-            umma_commit(a_empty(sa));
-          }
-          __syncwarp();
-        } else {
-#pragma unroll 1
-          for (int t = 0; t < p.n_taps; ++t) {
-            mbar_wait(b_full(sb), pb);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t b_lo = desc_lo_sw128(b_base + sb * b_stage_bytes, 16);
-              const uint32_t a_t = a_lo + static_cast<uint32_t>(p.tap_row[t]) * 8u;
-#pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                if (mt < p.MT) {
-#pragma unroll
-                  for (int j = 0; j < kBlockK / 16; ++j)
-                    umma_bf16_lohi(d_tmem + mt * bn, a_t + mt * mt_off + 2u * j, a_hi, b_lo + 2u * j,
-                                   b_hi, idesc, (cg | t | j) != 0 ? 1u : 0u);
-                }
-              }
-              umma_commit(b_empty(sb));
-              if (t == p.n_taps - 1) umma_commit(a_empty(sa));
-            }
-            __syncwarp();
-            if (++sb == static_cast<uint32_t>(SB)) {
-              sb = 0;
-              pb ^= 1u;
-            }
-          }
-        }
-        if (++sa == static_cast<uint32_t>(SA)) {
-          sa = 0;
-          pa ^= 1u;
-        }
-      }
-      if (elect_one()) umma_commit(tfull_bar(acc));
-      __syncwarp();
-      first = false;
-    }
+    // (specialised on taps / accumulators / N tile: the issue loop must cost well under one MMA
+    // time -- 32..64 cycles -- per instruction or the tensor pipe starves; see halo_mma_issuer)
+    const HaloIssueCtx c{smem_base, b_base, bar_base, tmem_base, u_begin, u_step, u_end, chunks_total};
+    if (p.n_taps == 9 && p.MT == 2 && p.BN == 64) halo_mma_issuer<9, 2, 64>(p, c);
+    else if (p.n_taps == 9 && p.MT == 2 && p.BN == 128) halo_mma_issuer<9, 2, 128>(p, c);
+    else if (p.n_taps == 9 && p.MT == 1 && p.BN == 64) halo_mma_issuer<9, 1, 64>(p, c);
+    else if (p.n_taps == 9 && p.MT == 1 && p.BN == 128) halo_mma_issuer<9, 1, 128>(p, c);
+    else halo_mma_issuer<0, 0, 0>(p, c);
   } else if (warp >= 4 && p.tma_epilogue) {
     // ------------------------------------------------------------ epilogue (TMA stores)
     // A "block" is one 64-channel column block of one 16-row accumulator: 128 rows x 128 B in

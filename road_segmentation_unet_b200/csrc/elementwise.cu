@@ -513,7 +513,7 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ v, long long 
 // sparse softmax cross-entropy (:103-110) and all gradients that leave this layer.
 // LP = C/8 lanes cooperate on one pixel (each owns 8 channels).
 template <int LP>
-__global__ void head_kernel(const uint4* __restrict__ act, long long pixels, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 3) head_kernel(const uint4* __restrict__ act, long long pixels, const float* __restrict__ w,
                             const float* __restrict__ b, const unsigned char* __restrict__ labels,
                             float* __restrict__ probs, float* __restrict__ logits,
                             float* __restrict__ loss, uint4* __restrict__ dZ, float* __restrict__ dW,
@@ -535,56 +535,69 @@ __global__ void head_kernel(const uint4* __restrict__ act, long long pixels, con
 
   const long long warp_global = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = (1LL * gridDim.x * blockDim.x) >> 5;
-  for (long long p0 = warp_global * PPW; p0 < pixels; p0 += n_warps * PPW) {
-    const long long p = p0 + pw;
-    const bool ok = p < pixels;
-    float a[8];
-    if (ok) unpack8(__ldg(act + p * LP + sub), a);
-    else {
+  // U pixel groups per iteration: all activation (and label) loads are issued before the first
+  // dependent instruction, which is what keeps enough bytes in flight for this HBM-bound kernel
+  constexpr int U = 4;
+  for (long long p0 = warp_global * (PPW * U); p0 < pixels; p0 += n_warps * (PPW * U)) {
+    uint4 raw[U];
+    int lab[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = 0.f;
-    }
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      l0 += a[e] * w0[e];
-      l1 += a[e] * w1[e];
-    }
-#pragma unroll
-    for (int o = LP / 2; o > 0; o >>= 1) {
-      l0 += __shfl_xor_sync(0xffffffffu, l0, o);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-    }
-    l0 += b0;
-    l1 += b1;
-    const float mx = fmaxf(l0, l1);
-    const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx);
-    const float inv = 1.f / (e0 + e1);
-    const float p1 = e1 * inv;
-    if (ok && sub == 0) {
-      if (probs) probs[p] = p1;
-      if (logits) {
-        logits[p * 2] = l0;
-        logits[p * 2 + 1] = l1;
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * PPW + pw;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      lab[u] = 0;
+      if (p < pixels) {
+        raw[u] = __ldg(act + p * LP + sub);
+        if (labels != nullptr) lab[u] = labels[p];
       }
     }
-    if (labels != nullptr && ok) {
-      const int lab = labels[p];
-      const float dl1 = (p1 - (lab ? 1.f : 0.f)) * inv_count;
-      const float dl0 = -dl1;  // (p0 - onehot0) = -(p1 - onehot1)
-      if (sub == 0) {
-        aloss += (mx + __logf(e0 + e1)) - (lab ? l1 : l0);
-        ab0 += dl0;
-        ab1 += dl1;
-      }
-      float gz[8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * PPW + pw;
+      const bool ok = p < pixels;
+      float a[8];
+      unpack8(raw[u], a);
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        aw0[e] += a[e] * dl0;
-        aw1[e] += a[e] * dl1;
-        gz[e] = a[e] > 0.f ? dl0 * w0[e] + dl1 * w1[e] : 0.f;
+        l0 += a[e] * w0[e];
+        l1 += a[e] * w1[e];
       }
-      dZ[p * LP + sub] = pack8(gz);
+#pragma unroll
+      for (int o = LP / 2; o > 0; o >>= 1) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+      }
+      l0 += b0;
+      l1 += b1;
+      const float mx = fmaxf(l0, l1);
+      const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx);
+      const float inv = 1.f / (e0 + e1);
+      const float p1 = e1 * inv;
+      if (ok && sub == 0) {
+        if (probs) probs[p] = p1;
+        if (logits) {
+          logits[p * 2] = l0;
+          logits[p * 2 + 1] = l1;
+        }
+      }
+      if (labels != nullptr && ok) {
+        const float dl1 = (p1 - (lab[u] ? 1.f : 0.f)) * inv_count;
+        const float dl0 = -dl1;  // (p0 - onehot0) = -(p1 - onehot1)
+        if (sub == 0) {
+          aloss += (mx + __logf(e0 + e1)) - (lab[u] ? l1 : l0);
+          ab0 += dl0;
+          ab1 += dl1;
+        }
+        float gz[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          aw0[e] += a[e] * dl0;
+          aw1[e] += a[e] * dl1;
+          gz[e] = a[e] > 0.f ? dl0 * w0[e] + dl1 * w1[e] : 0.f;
+        }
+        dZ[p * LP + sub] = pack8(gz);
+      }
     }
   }
   if (labels == nullptr) return;

@@ -1,47 +1,100 @@
 // Geometry kernels replacing the NumPy / SciPy helpers of src/images.py (fp32 images, NHWC).
 // All of them are pure data movement (bit-exact against the reference) except the two
 // averaging kernels, which accumulate in fp64 in the reference's summation order.
+//
+// They are HBM-bound, so every kernel is built around bytes in flight: one block per image row
+// (or 32 x 32 tile), 32-bit index arithmetic, 16-byte accesses where the row alignment allows it
+// and several independent loads issued per thread before the first use.
 #include "host_common.h"
 
 namespace rsu {
 
-static int geo_grid(long long items, int threads) {
-  long long blocks = (items + threads - 1) / threads;
-  const long long cap = 1LL * num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return static_cast<int>(blocks);
-}
-
-// np.pad(..., "symmetric") index: reflect with the edge sample repeated, period 2*L.
+// np.pad(..., "symmetric") index: reflect with the edge sample repeated, period 2*L.  The
+// extension is symmetric about -1/2, so f(-1 - j) = f(j); the modulo only runs when the pad is
+// wider than the image.
 __device__ __forceinline__ int sym_index(int i, int L) {
-  int m = i % (2 * L);
-  if (m < 0) m += 2 * L;
-  return m < L ? m : 2 * L - 1 - m;
+  if (i < 0) i = -1 - i;
+  if (i >= L) {
+    const int m = i % (2 * L);
+    i = m < L ? m : 2 * L - 1 - m;
+  }
+  return i;
 }
 
-// images.mirror_border (images.py:269-281)
-__global__ void mirror_pad_kernel(const float* __restrict__ in, int N, int H, int W, int C, int pad,
-                                  float* __restrict__ out) {
+__device__ __forceinline__ bool aligned16(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+// images.mirror_border (images.py:269-281).  One block per output row; a thread moves groups of
+// four consecutive floats: interior groups are one 16-byte load (source contiguous) and border
+// groups four reflected scalar loads; stores are 16 bytes.  VEC = 0: rows whose length or base
+// is not 16-byte aligned use the same walk with scalar accesses.
+template <int C_T, int VEC>
+__global__ void __launch_bounds__(256)
+    mirror_pad_kernel(const float* __restrict__ in, int H, int W, int C_rt, int pad,
+                      float* __restrict__ out) {
+  const int C = C_T ? C_T : C_rt;
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
-  const long long row_elems = 1LL * Wo * C;
-  const long long total = 1LL * N * Ho * row_elems;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
-       i += 1LL * gridDim.x * blockDim.x) {
-    const int xc = static_cast<int>(i % row_elems);
-    const int x = xc / C, c = xc - x * C;
-    const int y = static_cast<int>((i / row_elems) % Ho);
-    const int n = static_cast<int>(i / (row_elems * Ho));
-    const int sy = sym_index(y - pad, H), sx = sym_index(x - pad, W);
-    out[i] = __ldg(in + ((1LL * n * H + sy) * W + sx) * C + c);
+  const int row = blockIdx.x;
+  const int n = row / Ho, y = row - n * Ho;
+  const int sy = sym_index(y - pad, H);
+  const float* __restrict__ src = in + (1LL * n * H + sy) * W * C;
+  float* __restrict__ dst = out + 1LL * row * Wo * C;
+  const int row_elems = Wo * C;
+  const int lo = pad * C, hi = (pad + W) * C;
+  auto fetch = [&](int e) -> float {
+    const int x = e / C, c = e - x * C;
+    return __ldg(src + sym_index(x - pad, W) * C + c);
+  };
+  if (VEC) {
+    const bool src_vec = aligned16(src);  // (lo is a multiple of 4 floats whenever VEC is chosen)
+    constexpr int U = 2;
+    const int n4 = row_elems >> 2;
+    for (int g0 = threadIdx.x; g0 < n4; g0 += blockDim.x * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = g0 + u * blockDim.x;
+        const int e = g << 2;
+        if (g < n4) {
+          if (e >= lo && e + 3 < hi && src_vec && ((e - lo) & 3) == 0) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + (e - lo)));
+          } else if (e >= lo && e + 3 < hi) {
+            const float* s = src + (e - lo);
+            v[u] = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), __ldg(s + 3));
+          } else {
+            v[u] = make_float4(fetch(e), fetch(e + 1), fetch(e + 2), fetch(e + 3));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = g0 + u * blockDim.x;
+        if (g < n4) reinterpret_cast<float4*>(dst)[g] = v[u];
+      }
+    }
+  } else {
+    constexpr int U = 8;
+    for (int e0 = threadIdx.x; e0 < row_elems; e0 += blockDim.x * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < row_elems) v[u] = (e >= lo && e < hi) ? __ldg(src + (e - lo)) : fetch(e);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < row_elems) dst[e] = v[u];
+      }
+    }
   }
 }
 
 // Dihedral-group transform of square images, one op per image:
 //   out = rot90(flipud(x) if (op & 4) else x, k = op & 3)     (counter-clockwise, like np.rot90)
-// A 32x32-pixel destination tile maps onto a 32x32 source tile; the source tile is read
-// row-wise (coalesced) into shared memory and written out row-wise in destination order.
-// words = 4-byte words per pixel.
+// A T x T-pixel destination tile maps onto a T x T source tile; the source tile is read row-wise
+// (coalesced) into shared memory and written out row-wise in destination order.
 __device__ __forceinline__ void d4_src(int op, int S, int i, int j, int* si, int* sj) {
   int a, b;
   switch (op & 3) {
@@ -55,21 +108,81 @@ __device__ __forceinline__ void d4_src(int op, int S, int i, int j, int* si, int
   *sj = b;
 }
 
+// source tile of the destination tile [i0, i0+T) x [j0, j0+T): origin and extent
+__device__ __forceinline__ void d4_src_tile(int op, int S, int i0, int j0, int i1, int j1, int* si0,
+                                            int* sj0, int* sh, int* sw) {
+  int ci[2], cj[2];
+  d4_src(op, S, i0, j0, &ci[0], &cj[0]);
+  d4_src(op, S, i1, j1, &ci[1], &cj[1]);
+  *si0 = min(ci[0], ci[1]);
+  *sj0 = min(cj[0], cj[1]);
+  *sh = abs(ci[0] - ci[1]) + 1;
+  *sw = abs(cj[0] - cj[1]) + 1;
+}
+
+// WORDS (elements of WordT per pixel) and T (tile side) are compile-time: every thread of the
+// 32 x 8 block issues all of its T/8 * T*WORDS/32 loads before the first shared-memory store.
+template <typename WordT, int WORDS, int T>
+__global__ void __launch_bounds__(256)
+    d4_transform_kernel(const WordT* __restrict__ in, WordT* __restrict__ out, int S,
+                        const unsigned char* __restrict__ ops) {
+  constexpr int RW = T * WORDS;     // words per tile row
+  constexpr int PITCH = RW + 1;
+  constexpr int QW = (RW + 31) / 32;
+  constexpr int QR = T / 8;
+  __shared__ WordT tile[T * PITCH];
+  const int n = blockIdx.z;
+  const int op = ops[n];
+  const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+  const int i1 = min(i0 + T - 1, S - 1), j1 = min(j0 + T - 1, S - 1);
+  int si0, sj0, sh, sw;
+  d4_src_tile(op, S, i0, j0, i1, j1, &si0, &sj0, &sh, &sw);
+  const WordT* __restrict__ src = in + (1LL * n * S + si0) * S * WORDS + 1LL * sj0 * WORDS;
+  WordT* __restrict__ dst = out + (1LL * n * S + i0) * S * WORDS + 1LL * j0 * WORDS;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  WordT v[QR][QW];
+#pragma unroll
+  for (int r = 0; r < QR; ++r)
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+      const int rr = ty + 8 * r, w = tx + 32 * q;
+      if (rr < sh && w < sw * WORDS) v[r][q] = __ldg(src + 1LL * rr * S * WORDS + w);
+    }
+#pragma unroll
+  for (int r = 0; r < QR; ++r)
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+      const int rr = ty + 8 * r, w = tx + 32 * q;
+      if (rr < sh && w < sw * WORDS) tile[rr * PITCH + w] = v[r][q];
+    }
+  __syncthreads();
+  const int th = i1 - i0 + 1, tw = j1 - j0 + 1;
+#pragma unroll
+  for (int r = 0; r < QR; ++r)
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+      const int rr = ty + 8 * r, w = tx + 32 * q;
+      if (rr < th && w < tw * WORDS) {
+        const int j = w / WORDS, e = w - j * WORDS;
+        int si, sj;
+        d4_src(op, S, i0 + rr, j0 + j, &si, &sj);
+        dst[1LL * rr * S * WORDS + w] = tile[(si - si0) * PITCH + (sj - sj0) * WORDS + e];
+      }
+    }
+}
+
+// any pixel size (fp64 images travel as 2 x 32-bit words per element): run-time word count
 template <typename WordT>
-__global__ void d4_transform_kernel(const WordT* __restrict__ in, WordT* __restrict__ out, int S,
-                                    int words, const unsigned char* __restrict__ ops) {
+__global__ void d4_transform_generic_kernel(const WordT* __restrict__ in, WordT* __restrict__ out,
+                                            int S, int words, const unsigned char* __restrict__ ops) {
   extern __shared__ uint8_t tile_raw[];  // [32][32*words + 1] words
   WordT* tile = reinterpret_cast<WordT*>(tile_raw);
   const int n = blockIdx.z;
   const int op = ops[n];
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  // source tile origin = min over the tile corners of the mapped coordinates
-  int ci[2], cj[2];
-  d4_src(op, S, i0, j0, &ci[0], &cj[0]);
   const int i1 = min(i0 + 31, S - 1), j1 = min(j0 + 31, S - 1);
-  d4_src(op, S, i1, j1, &ci[1], &cj[1]);
-  const int si0 = min(ci[0], ci[1]), sj0 = min(cj[0], cj[1]);
-  const int sh = abs(ci[0] - ci[1]) + 1, sw = abs(cj[0] - cj[1]) + 1;
+  int si0, sj0, sh, sw;
+  d4_src_tile(op, S, i0, j0, i1, j1, &si0, &sj0, &sh, &sw);
   const int pitch = 32 * words + 1;
   const WordT* src = in + 1LL * n * S * S * words;
   WordT* dst = out + 1LL * n * S * S * words;
@@ -88,58 +201,100 @@ __global__ void d4_transform_kernel(const WordT* __restrict__ in, WordT* __restr
 }
 
 // images.extract_patches (images.py:35-85): patch k of image n sits at column (k / side)*stride,
-// row (k % side)*stride  (x is the OUTER loop in the reference).
-__global__ void extract_patches_kernel(const float* __restrict__ in, int N, int H, int W, int C,
-                                       int P, int stride, int side, long long k_begin,
-                                       long long k_count, float* __restrict__ out) {
-  const long long row_elems = 1LL * P * C;
-  const long long total = k_count * P * row_elems;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
-       i += 1LL * gridDim.x * blockDim.x) {
-    const int xc = static_cast<int>(i % row_elems);
-    const int py = static_cast<int>((i / row_elems) % P);
-    const long long k_all = k_begin + i / (row_elems * P);
-    const int k = static_cast<int>(k_all % (side * side));
-    const int n = static_cast<int>(k_all / (side * side));
-    const int x0 = (k / side) * stride, y0 = (k % side) * stride;
-    out[i] = __ldg(in + ((1LL * n * H + y0 + py) * W + x0) * C + xc);
+// row (k % side)*stride  (x is the OUTER loop in the reference).  One block per patch row: the
+// source is a contiguous run of P*C floats, moved 16 bytes at a time when both ends allow it.
+template <int VEC>
+__global__ void __launch_bounds__(128)
+    extract_patches_kernel(const float* __restrict__ in, int H, int W, int C, int P, int stride,
+                           int side, long long k_begin, float* __restrict__ out) {
+  const int row = blockIdx.x;  // (local patch, patch row)
+  const int kl = row / P, py = row - kl * P;
+  const long long k_all = k_begin + kl;
+  const int per_img = side * side;
+  const int n = static_cast<int>(k_all / per_img);
+  const int k = static_cast<int>(k_all - 1LL * n * per_img);
+  const int kx = k / side, ky = k - kx * side;
+  const float* __restrict__ src = in + ((1LL * n * H + ky * stride + py) * W + kx * stride) * C;
+  float* __restrict__ dst = out + 1LL * row * P * C;
+  const int n_el = P * C;
+  if (VEC && aligned16(src)) {  // (dst rows are 16-byte aligned whenever VEC is chosen)
+    constexpr int U = 4;
+    const int n4 = n_el >> 2;
+    for (int g0 = threadIdx.x; g0 < n4; g0 += blockDim.x * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = g0 + u * blockDim.x;
+        if (g < n4) v[u] = __ldg(reinterpret_cast<const float4*>(src) + g);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = g0 + u * blockDim.x;
+        if (g < n4) reinterpret_cast<float4*>(dst)[g] = v[u];
+      }
+    }
+  } else {
+    constexpr int U = 8;
+    for (int e0 = threadIdx.x; e0 < n_el; e0 += blockDim.x * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < n_el) v[u] = __ldg(src + e);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < n_el) dst[e] = v[u];
+      }
+    }
   }
 }
 
 // images.images_from_patches (images.py:131-164) in gather form: every output pixel sums the
 // patches covering it in the reference's order (x outer, y inner) in fp64 and divides by the
-// hit count -- deterministic, no atomics.
+// hit count -- deterministic, no atomics.  Eight loads of the inner loop are issued together.
 // k_lo/k_hi restrict the sum to patches whose global index (n*side*side + k) lies in
 // [k_lo, k_hi) -- a rank of a sharded prediction holds only that slice (patches points at patch
 // k_lo) and emits partial sums (normalize = 0) that are added and divided after the gather.
-__global__ void overlap_average_kernel(const float* __restrict__ patches, int N, int side, int P,
-                                       int C, int stride, int S, long long k_lo, long long k_hi,
-                                       int normalize, float* __restrict__ out) {
-  const long long row_elems = 1LL * S * C;
-  const long long total = 1LL * N * S * row_elems;
+__global__ void __launch_bounds__(128)
+    overlap_average_kernel(const float* __restrict__ patches, int side, int P, int C, int stride,
+                           int S, long long k_lo, long long k_hi, int normalize,
+                           float* __restrict__ out) {
+  const int row = blockIdx.x;  // n*S + y
+  const int n = row / S, y = row - n * S;
+  const int row_elems = S * C;
   const long long patch_elems = 1LL * P * P * C;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
-       i += 1LL * gridDim.x * blockDim.x) {
-    const int xc = static_cast<int>(i % row_elems);
+  int ky_lo = (y - P + stride) / stride;  // ceil((y-P+1)/stride)
+  if (y - P + 1 <= 0) ky_lo = 0;
+  const int ky_hi = min(y / stride, side - 1);
+  const long long img_k0 = 1LL * n * side * side;
+  constexpr int U = 8;
+  for (int xc = blockIdx.y * blockDim.x + threadIdx.x; xc < row_elems; xc += gridDim.y * blockDim.x) {
     const int x = xc / C, c = xc - x * C;
-    const int y = static_cast<int>((i / row_elems) % S);
-    const int n = static_cast<int>(i / (row_elems * S));
-    int kx_lo = (x - P + stride) / stride;  // ceil((x-P+1)/stride)
+    int kx_lo = (x - P + stride) / stride;
     if (x - P + 1 <= 0) kx_lo = 0;
-    int ky_lo = (y - P + stride) / stride;
-    if (y - P + 1 <= 0) ky_lo = 0;
-    const int kx_hi = min(x / stride, side - 1), ky_hi = min(y / stride, side - 1);
+    const int kx_hi = min(x / stride, side - 1);
     double acc = 0.0;
-    const long long img_k0 = 1LL * n * side * side;
-    for (int kx = kx_lo; kx <= kx_hi; ++kx)
-      for (int ky = ky_lo; ky <= ky_hi; ++ky) {
-        const long long k = img_k0 + kx * side + ky;
-        if (k < k_lo || k >= k_hi) continue;
-        acc += static_cast<double>(__ldg(patches + (k - k_lo) * patch_elems +
-                                         (1LL * (y - ky * stride) * P + (x - kx * stride)) * C + c));
+    for (int kx = kx_lo; kx <= kx_hi; ++kx) {
+      const long long kcol = img_k0 + 1LL * kx * side;
+      const float* __restrict__ base = patches + (kcol - k_lo) * patch_elems +
+                                       (1LL * y * P + (x - kx * stride)) * C + c;
+      const long long ky_step = patch_elems - 1LL * stride * P * C;  // next ky: next patch, stride rows up
+      for (int ky0 = ky_lo; ky0 <= ky_hi; ky0 += U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int ky = ky0 + u;
+          const long long k = kcol + ky;
+          v[u] = (ky <= ky_hi && k >= k_lo && k < k_hi) ? __ldg(base + ky * ky_step) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += static_cast<double>(v[u]);
       }
+    }
     const int cnt = (kx_hi - kx_lo + 1) * (ky_hi - ky_lo + 1);
-    out[i] = static_cast<float>(normalize ? acc / static_cast<double>(cnt) : acc);
+    out[1LL * row * row_elems + xc] = static_cast<float>(normalize ? acc / static_cast<double>(cnt) : acc);
   }
 }
 
@@ -147,57 +302,87 @@ __global__ void overlap_average_kernel(const float* __restrict__ patches, int N,
 // order=0, reshape=True, mode='constant', cval=0: output pixel o maps to input coordinate
 // R*o + offset (fp64); the sample is in[floor(y+0.5), floor(x+0.5)] when the unrounded
 // coordinate lies in [0, H-1] on both axes, else 0.  Only the centre crop is ever materialised.
+// One thread per output pixel (the fp64 coordinate is shared by the C channels); a block covers
+// a 32 x 8 pixel patch so that the gathered source pixels share cache lines.
 struct RotParams {
   double m00, m01, m10, m11, off0, off1;
   int out_side, crop0;
 };
-__global__ void rotate_nn_crop_kernel(const float* __restrict__ in, int N, int H, int C, RotParams rp,
-                                      int crop, float* __restrict__ out) {
-  const long long row_elems = 1LL * crop * C;
-  const long long total = 1LL * N * crop * row_elems;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
-       i += 1LL * gridDim.x * blockDim.x) {
-    const int xc = static_cast<int>(i % row_elems);
-    const int x = xc / C, c = xc - x * C;
-    const int y = static_cast<int>((i / row_elems) % crop);
-    const int n = static_cast<int>(i / (row_elems * crop));
-    const double oy = static_cast<double>(y + rp.crop0), ox = static_cast<double>(x + rp.crop0);
-    // SciPy's NI_GeometricTransform order: cc = shift; cc += o[0]*m[i][0]; cc += o[1]*m[i][1]
-    // (explicit _rn intrinsics: no FMA contraction, so ties resolve exactly as on the CPU)
-    const double iy = __dadd_rn(__dadd_rn(rp.off0, __dmul_rn(oy, rp.m00)), __dmul_rn(ox, rp.m01));
-    const double ix = __dadd_rn(__dadd_rn(rp.off1, __dmul_rn(oy, rp.m10)), __dmul_rn(ox, rp.m11));
-    const long long ry = static_cast<long long>(floor(iy + 0.5));
-    const long long rx = static_cast<long long>(floor(ix + 0.5));
-    float v = 0.f;
-    // mode='constant' is decided on the unrounded coordinate: outside [0, H-1] -> cval
-    const double hi = static_cast<double>(H - 1);
-    if (iy >= 0.0 && iy <= hi && ix >= 0.0 && ix <= hi)
-      v = __ldg(in + ((1LL * n * H + ry) * H + rx) * C + c);
-    out[i] = v;
+template <int C_T>
+__global__ void __launch_bounds__(256)
+    rotate_nn_crop_kernel(const float* __restrict__ in, int H, int C_rt, RotParams rp, int crop,
+                          float* __restrict__ out) {
+  const int C = C_T ? C_T : C_rt;
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= crop || y >= crop) return;
+  const double oy = static_cast<double>(y + rp.crop0), ox = static_cast<double>(x + rp.crop0);
+  // SciPy's NI_GeometricTransform order: cc = shift; cc += o[0]*m[i][0]; cc += o[1]*m[i][1]
+  // (explicit _rn intrinsics: no FMA contraction, so ties resolve exactly as on the CPU)
+  const double iy = __dadd_rn(__dadd_rn(rp.off0, __dmul_rn(oy, rp.m00)), __dmul_rn(ox, rp.m01));
+  const double ix = __dadd_rn(__dadd_rn(rp.off1, __dmul_rn(oy, rp.m10)), __dmul_rn(ox, rp.m11));
+  // mode='constant' is decided on the unrounded coordinate: outside [0, H-1] -> cval
+  const double hi = static_cast<double>(H - 1);
+  const bool inside = iy >= 0.0 && iy <= hi && ix >= 0.0 && ix <= hi;
+  const long long ry = static_cast<long long>(floor(iy + 0.5));
+  const long long rx = static_cast<long long>(floor(ix + 0.5));
+  const float* __restrict__ s = in + ((1LL * n * H + ry) * H + rx) * C;
+  float* __restrict__ d = out + ((1LL * n * crop + y) * crop + x) * C;
+  if (C_T) {
+    float v[C_T ? C_T : 1];
+#pragma unroll
+    for (int c = 0; c < C_T; ++c) v[c] = inside ? __ldg(s + c) : 0.f;
+#pragma unroll
+    for (int c = 0; c < C_T; ++c) d[c] = v[c];
+  } else {
+    for (int c = 0; c < C; ++c) d[c] = inside ? __ldg(s + c) : 0.f;
   }
 }
 
 // images.invert_image_augmentation_ensemble (images.py:399-417): undo the 6 variants and average
-// (fp64 accumulation in the reference's order).
-__global__ void ensemble_invert_kernel(const float* __restrict__ masks, int N, int S,
-                                       float* __restrict__ out) {
+// (fp64 accumulation in the reference's order).  Per 32 x 32 output tile the six source tiles
+// are read row-wise (coalesced, also for the transposing variants) into shared memory.
+__global__ void __launch_bounds__(256)
+    ensemble_invert_kernel(const float* __restrict__ masks, int N, int S, float* __restrict__ out) {
+  __shared__ float t[6][32][33];
+  const int n = blockIdx.z;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int i1 = min(i0 + 31, S - 1), j1 = min(j0 + 31, S - 1);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  // variant v -> inverse op: 0 id, 1 fliplr (=flipud+rot180), 2 flipud, 3 rot90^-1, 4 rot90^-2, 5 rot90^-3
+  const int inv_ops[6] = {0, 4 | 2, 4, 3, 2, 1};
   const long long img = 1LL * S * S;
-  const long long total = 1LL * N * img;
-  for (long long idx = blockIdx.x * 1LL * blockDim.x + threadIdx.x; idx < total;
-       idx += 1LL * gridDim.x * blockDim.x) {
-    const int j = static_cast<int>(idx % S);
-    const int i = static_cast<int>((idx / S) % S);
-    const int n = static_cast<int>(idx / img);
-    // variant v -> inverse op: 0 id, 1 fliplr (=flipud+rot180), 2 flipud, 3 rot90^-1, 4 rot90^-2, 5 rot90^-3
-    const int inv_ops[6] = {0, 4 | 2, 4, 3, 2, 1};
-    double acc = 0.0;
+  float v[6][4];
+  int si0[6], sj0[6];
 #pragma unroll
-    for (int v = 0; v < 6; ++v) {
-      int si, sj;
-      d4_src(inv_ops[v], S, i, j, &si, &sj);
-      acc += static_cast<double>(__ldg(masks + (1LL * v * N + n) * img + 1LL * si * S + sj));
+  for (int k = 0; k < 6; ++k) {
+    int sh, sw;
+    d4_src_tile(inv_ops[k], S, i0, j0, i1, j1, &si0[k], &sj0[k], &sh, &sw);
+    const float* __restrict__ src = masks + (1LL * k * N + n) * img + 1LL * si0[k] * S + sj0[k];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int rr = ty + 8 * r;
+      v[k][r] = (rr < sh && tx < sw) ? __ldg(src + 1LL * rr * S + tx) : 0.f;
     }
-    out[idx] = static_cast<float>(acc / 6.0);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) t[k][ty + 8 * r][tx] = v[k][r];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + 8 * r, j = j0 + tx;
+    if (i <= i1 && j <= j1) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        int si, sj;
+        d4_src(inv_ops[k], S, i, j, &si, &sj);
+        acc += static_cast<double>(t[k][si - si0[k]][sj - sj0[k]]);
+      }
+      out[n * img + 1LL * i * S + j] = static_cast<float>(acc / 6.0);
+    }
   }
 }
 
@@ -209,8 +394,23 @@ extern "C" {
 
 int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* out, void* stream) {
   if (N < 1 || H < 1 || W < 1 || C < 1 || pad < 0) return set_error(RSU_EINVAL, "mirror_pad: shape");
-  const long long total = 1LL * N * (H + 2 * pad) * (W + 2 * pad) * C;
-  mirror_pad_kernel<<<geo_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, N, H, W, C, pad, out);
+  const long long rows = 1LL * N * (H + 2 * pad);
+  if (rows > 0x7fffffffLL || 1LL * (W + 2 * pad) * C > 0x7fffffffLL)
+    return set_error(RSU_EINVAL, "mirror_pad: more than 2^31 rows / row elements");
+  const bool vec = ((W + 2 * pad) * C) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const dim3 grid(static_cast<unsigned>(rows));
+  cudaStream_t st = (cudaStream_t)stream;
+#define RSU_MP(CT, V) mirror_pad_kernel<CT, V><<<grid, 256, 0, st>>>(in, H, W, C, pad, out)
+  if (vec) {
+    if (C == 3) RSU_MP(3, 1);
+    else if (C == 1) RSU_MP(1, 1);
+    else RSU_MP(0, 1);
+  } else {
+    if (C == 3) RSU_MP(3, 0);
+    else if (C == 1) RSU_MP(1, 0);
+    else RSU_MP(0, 0);
+  }
+#undef RSU_MP
   return check_launch("mirror_pad");
 }
 
@@ -220,19 +420,30 @@ int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
     return set_error(RSU_EINVAL, "d4_transform: bad shape N=%d S=%d pixel_bytes=%d", N, S, pixel_bytes);
   if (in == out) return set_error(RSU_EINVAL, "d4_transform: in-place not supported");
   if (N > 65535) return set_error(RSU_EINVAL, "d4_transform: N > 65535");
-  dim3 grid((S + 31) / 32, (S + 31) / 32, N), block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 block(32, 8);
+  const dim3 g32((S + 31) / 32, (S + 31) / 32, N), g64((S + 63) / 64, (S + 63) / 64, N);
   const bool word4 = pixel_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 3) == 0;
-  if (word4) {
+  if (word4 && pixel_bytes == 12) {  // RGB fp32
+    d4_transform_kernel<uint32_t, 3, 32><<<g32, block, 0, st>>>(
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops);
+  } else if (word4 && pixel_bytes == 4) {  // fp32 masks
+    d4_transform_kernel<uint32_t, 1, 64><<<g64, block, 0, st>>>(
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops);
+  } else if (pixel_bytes == 1) {  // uint8 label masks
+    d4_transform_kernel<uint8_t, 1, 64><<<g64, block, 0, st>>>(
+        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, ops);
+  } else if (word4) {
     const int words = pixel_bytes / 4;
     const size_t smem = 32 * (32 * words + 1) * sizeof(uint32_t);
     if (smem > 48 * 1024) return set_error(RSU_EINVAL, "d4_transform: pixel too large");
-    d4_transform_kernel<uint32_t><<<grid, block, smem, (cudaStream_t)stream>>>(
+    d4_transform_generic_kernel<uint32_t><<<g32, block, smem, st>>>(
         static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, words, ops);
-  } else {  // byte-granular pixels (uint8 label masks)
+  } else {  // byte-granular pixels
     const size_t smem = 32 * (32 * pixel_bytes + 1);
     if (smem > 48 * 1024) return set_error(RSU_EINVAL, "d4_transform: pixel too large");
-    d4_transform_kernel<uint8_t><<<grid, block, smem, (cudaStream_t)stream>>>(
+    d4_transform_generic_kernel<uint8_t><<<g32, block, smem, st>>>(
         static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, pixel_bytes, ops);
   }
   return check_launch("d4_transform");
@@ -249,9 +460,16 @@ int rsu_extract_patches(const float* in, int N, int H, int W, int C, int patch, 
   if (k_begin < 0 || k_begin + k_count > all || k_count < 1)
     return set_error(RSU_EINVAL, "extract_patches: patch range [%lld, +%lld) outside %lld", k_begin,
                      k_count, all);
-  const long long total = k_count * patch * patch * C;
-  extract_patches_kernel<<<geo_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      in, N, H, W, C, patch, stride, side, k_begin, k_count, out);
+  const long long rows = k_count * patch;
+  if (rows > 0x7fffffffLL) return set_error(RSU_EINVAL, "extract_patches: more than 2^31 patch rows");
+  const bool vec = (patch * C) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const dim3 grid(static_cast<unsigned>(rows));
+  if (vec)
+    extract_patches_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(in, H, W, C, patch, stride, side,
+                                                                      k_begin, out);
+  else
+    extract_patches_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(in, H, W, C, patch, stride, side,
+                                                                      k_begin, out);
   return check_launch("extract_patches");
 }
 
@@ -265,9 +483,13 @@ int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int
   if (k_begin < 0 || k_begin + k_count > all)
     return set_error(RSU_EINVAL, "overlap_average: patch range outside [0, %lld)", all);
   const int S = (side - 1) * stride + P;
-  const long long total = 1LL * N * S * S * C;
-  overlap_average_kernel<<<geo_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      patches, N, side, P, C, stride, S, k_begin, k_begin + k_count, normalize, out);
+  const long long rows = 1LL * N * S;
+  if (rows > 0x7fffffffLL) return set_error(RSU_EINVAL, "overlap_average: more than 2^31 rows");
+  int gy = (S * C + 127) / 128;
+  if (gy > 65535) gy = 65535;
+  const dim3 grid(static_cast<unsigned>(rows), gy);
+  overlap_average_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(patches, side, P, C, stride, S, k_begin,
+                                                                 k_begin + k_count, normalize, out);
   return check_launch("overlap_average");
 }
 
@@ -275,6 +497,7 @@ int rsu_rotate_nn_crop(const float* in, int N, int H, int C, const double* matri
                        const double* offset_host, int crop0, int crop, float* out, void* stream) {
   if (N < 1 || H < 1 || C < 1 || crop < 1 || crop0 < 0)
     return set_error(RSU_EINVAL, "rotate_nn_crop: shape");
+  if (N > 65535) return set_error(RSU_EINVAL, "rotate_nn_crop: N > 65535");
   RotParams rp;
   rp.m00 = matrix_host[0];
   rp.m01 = matrix_host[1];
@@ -284,16 +507,21 @@ int rsu_rotate_nn_crop(const float* in, int N, int H, int C, const double* matri
   rp.off1 = offset_host[1];
   rp.out_side = 0;
   rp.crop0 = crop0;
-  const long long total = 1LL * N * crop * crop * C;
-  rotate_nn_crop_kernel<<<geo_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, N, H, C, rp, crop,
-                                                                               out);
+  const dim3 grid((crop + 31) / 32, (crop + 7) / 8, N), block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 3) rotate_nn_crop_kernel<3><<<grid, block, 0, st>>>(in, H, C, rp, crop, out);
+  else if (C == 1) rotate_nn_crop_kernel<1><<<grid, block, 0, st>>>(in, H, C, rp, crop, out);
+  else if (C == 6) rotate_nn_crop_kernel<6><<<grid, block, 0, st>>>(in, H, C, rp, crop, out);
+  else if (C == 2) rotate_nn_crop_kernel<2><<<grid, block, 0, st>>>(in, H, C, rp, crop, out);
+  else rotate_nn_crop_kernel<0><<<grid, block, 0, st>>>(in, H, C, rp, crop, out);
   return check_launch("rotate_nn_crop");
 }
 
 int rsu_ensemble_invert(const float* masks, int N, int S, float* out, void* stream) {
   if (N < 1 || S < 1) return set_error(RSU_EINVAL, "ensemble_invert: shape");
-  ensemble_invert_kernel<<<geo_grid(1LL * N * S * S, 256), 256, 0, (cudaStream_t)stream>>>(masks, N, S,
-                                                                                            out);
+  if (N > 65535) return set_error(RSU_EINVAL, "ensemble_invert: N > 65535");
+  const dim3 grid((S + 31) / 32, (S + 31) / 32, N), block(32, 8);
+  ensemble_invert_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(masks, N, S, out);
   return check_launch("ensemble_invert");
 }
 

@@ -178,6 +178,16 @@ __global__ void __launch_bounds__(kWhThreads, 1)
     const uint32_t kstep16 = static_cast<uint32_t>(2 * p.Wh) * 8u;
     uint32_t stage = 0, phase = 0;
     uint32_t unit_it = 0;
+    const uint32_t stage16 = stage_bytes >> 4;
+    const uint32_t a16_base = (smem_base >> 4) & 0x3FFFu;
+    const uint32_t b_off16 = p.a_stage_bytes >> 4;
+    const uint32_t ones16 = (ones_base >> 4) & 0x3FFFu;
+    const uint32_t b_lbo = static_cast<uint32_t>(kWhBBytes >> 4) << 16;
+    // per-K-step advance of every accumulator's A descriptor: + kstep16 in the start address; the
+    // odd tile's second atom is the ones block, whose distance (LBO field) shrinks by as much
+    const uint32_t d_pair = kstep16;
+    const uint32_t d_last = odd ? kstep16 - (kstep16 << 16) : kstep16;
+    uint32_t a16 = a16_base;  // start address >> 4 of the current stage
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++unit_it) {
       int cg, n_tile, pt0, pt1;
       unit_range(unit, &cg, &n_tile, &pt0, &pt1);
@@ -187,29 +197,46 @@ __global__ void __launch_bounds__(kWhThreads, 1)
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_stage = smem_base + stage * stage_bytes;
-          const uint32_t a16 = (a_stage >> 4) & 0x3FFFu;
-          const uint32_t b16 = ((a_stage + p.a_stage_bytes) >> 4) & 0x3FFFu;
-          const uint32_t ones16 = (ones_base >> 4) & 0x3FFFu;
           const uint32_t acc = pt != pt0 ? 1u : 0u;
+          const uint32_t b_lo0 = a16 + b_off16 + b_lbo;
+          if (p.n_taps == 9) {
+            // 5 accumulators: 4 tap pairs + (tap 8, ones); everything but a16 is loop invariant
+            uint32_t a_lo[5];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // 16 pixels (two image rows of the tile) per instruction
-            const uint32_t b_lo = b16 + j * 128u + ((kWhBBytes >> 4) << 16);
+            for (int i = 0; i < 4; ++i) a_lo[i] = a16 + tile_lo[i];
+            {
+              const uint32_t x = a16 + (tile_lo[4] & 0xFFFFu);
+              a_lo[4] = x + ((ones16 - x) << 16);
+            }
 #pragma unroll
-            for (int i = 0; i < kMaxM; ++i) {
-              if (i < n_mtiles) {
-                uint32_t a_lo = a16 + tile_lo[i] + j * kstep16;
-                if (odd && i == n_mtiles - 1) a_lo += (ones16 - (a_lo & 0x3FFFu)) << 16;
-                umma_bf16_lohi(tmem_base + i * 64, a_lo, a_hi, b_lo, b_hi, idesc, j != 0 ? 1u : acc);
+            for (int j = 0; j < 8; ++j) {  // 16 pixels (two image rows of the tile) per instruction
+#pragma unroll
+              for (int i = 0; i < 5; ++i)
+                umma_bf16_lohi(tmem_base + i * 64, a_lo[i] + j * (i == 4 ? d_last : d_pair), a_hi,
+                               b_lo0 + j * 128u, b_hi, idesc, j != 0 ? 1u : acc);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t b_lo = b_lo0 + j * 128u;
+#pragma unroll
+              for (int i = 0; i < kMaxM; ++i) {
+                if (i < n_mtiles) {
+                  uint32_t a_lo = a16 + tile_lo[i] + j * kstep16;
+                  if (odd && i == n_mtiles - 1) a_lo += (ones16 - (a_lo & 0x3FFFu)) << 16;
+                  umma_bf16_lohi(tmem_base + i * 64, a_lo, a_hi, b_lo, b_hi, idesc, j != 0 ? 1u : acc);
+                }
               }
             }
           }
           umma_commit(empty_bar(stage));
         }
         __syncwarp();
+        a16 += stage16;
         if (++stage == static_cast<uint32_t>(stages)) {
           stage = 0;
           phase ^= 1u;
+          a16 = a16_base;
         }
       }
       if (elect_one()) umma_commit(tfull_bar);

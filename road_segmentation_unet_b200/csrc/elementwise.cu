@@ -89,7 +89,7 @@ struct PackJobDev {
   int block_begin, block_count;
 };
 __global__ void pack_batch_kernel(const PackJobDev* __restrict__ jobs, int n_jobs) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   __shared__ int s_job;
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     int lo = 0, hi = n_jobs - 1;
@@ -106,31 +106,75 @@ __global__ void pack_batch_kernel(const PackJobDev* __restrict__ jobs, int n_job
   const int lb = blockIdx.x - j.block_begin;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (j.kind == 0) {
-    const int tiles_c = (j.C + 31) / 32, tiles_r = (j.R + 31) / 32;
+    // [T][R][C] fp32 -> [C][ld] bf16 (row t*R + r): tiles of 64 r x 32 c; eight coalesced loads
+    // per thread, then every warp writes 64 consecutive bf16 (128 bytes) of one output row
+    const int tiles_c = (j.C + 31) / 32, tiles_r = (j.R + 63) / 64;
     const int t = lb / (tiles_c * tiles_r);
     const int rem = lb % (tiles_c * tiles_r);
-    const int c0 = (rem % tiles_c) * 32, r0 = (rem / tiles_c) * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < j.R && c < j.C) tile[i][threadIdx.x] = j.in[(static_cast<long long>(t) * j.R + r) * j.C + c];
+    const int c0 = (rem % tiles_c) * 32, r0 = (rem / tiles_c) * 64;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + threadIdx.y + 8 * i, c = c0 + threadIdx.x;
+      v[i] = (r < j.R && c < j.C) ? __ldg(j.in + (static_cast<long long>(t) * j.R + r) * j.C + c) : 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[threadIdx.y + 8 * i][threadIdx.x] = v[i];
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < j.R && c < j.C)
-        j.out[static_cast<long long>(c) * j.ld + t * j.R + r] = __float2bfloat16(tile[threadIdx.x][i]);
+    const bool pair_ok = ((j.ld | (t * j.R + r0)) & 1) == 0 && (reinterpret_cast<uintptr_t>(j.out) & 3) == 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + threadIdx.y + 8 * i, r = r0 + 2 * threadIdx.x;
+      if (c < j.C) {
+        __nv_bfloat16* o = j.out + static_cast<long long>(c) * j.ld + t * j.R + r;
+        const float a0 = tile[2 * threadIdx.x][threadIdx.y + 8 * i];
+        const float a1 = tile[2 * threadIdx.x + 1][threadIdx.y + 8 * i];
+        if (pair_ok && r + 1 < j.R) {
+          *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(a0, a1);
+        } else {
+          if (r < j.R) o[0] = __float2bfloat16(a0);
+          if (r + 1 < j.R) o[1] = __float2bfloat16(a1);
+        }
+      }
     }
   } else {
     const long long total = 1LL * j.T * j.R * j.C;
-    for (long long i = lb * 256LL + tid; i < total; i += 256LL * j.block_count) {
-      if (j.kind == 2) {
-        j.out[i] = __float2bfloat16(j.in[i]);
-      } else {
-        const int c = static_cast<int>(i % j.C);
-        const long long tr = i / j.C;
-        const int r = static_cast<int>(tr % j.R);
-        const int t = static_cast<int>(tr / j.R);
-        j.out[(static_cast<long long>(r) * j.T + t) * j.C + c] = __float2bfloat16(j.in[i]);
+    const bool vec = (j.C % 8 == 0 || j.kind == 2) && total % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(j.in) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(j.out) & 15) == 0;
+    if (vec) {
+      // eight consecutive elements (same t, r; consecutive c) per thread: 2 x 16 B in, 16 B out
+      const long long total8 = total >> 3;
+      const int c8n = j.C >> 3;
+      for (long long i8 = lb * 256LL + tid; i8 < total8; i8 += 256LL * j.block_count) {
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(j.in) + 2 * i8);
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(j.in) + 2 * i8 + 1);
+        uint4 o;
+        o.x = pack_bf16x2(f0.x, f0.y);
+        o.y = pack_bf16x2(f0.z, f0.w);
+        o.z = pack_bf16x2(f1.x, f1.y);
+        o.w = pack_bf16x2(f1.z, f1.w);
+        long long dst8 = i8;
+        if (j.kind != 2) {
+          const int c8 = static_cast<int>(i8 % c8n);
+          const long long tr = i8 / c8n;
+          const int r = static_cast<int>(tr % j.R);
+          const int t = static_cast<int>(tr / j.R);
+          dst8 = (static_cast<long long>(r) * j.T + t) * c8n + c8;
+        }
+        reinterpret_cast<uint4*>(j.out)[dst8] = o;
+      }
+    } else {
+      for (long long i = lb * 256LL + tid; i < total; i += 256LL * j.block_count) {
+        if (j.kind == 2) {
+          j.out[i] = __float2bfloat16(j.in[i]);
+        } else {
+          const int c = static_cast<int>(i % j.C);
+          const long long tr = i / j.C;
+          const int r = static_cast<int>(tr % j.R);
+          const int t = static_cast<int>(tr / j.R);
+          j.out[(static_cast<long long>(r) * j.T + t) * j.C + c] = __float2bfloat16(j.in[i]);
+        }
       }
     }
   }
@@ -387,14 +431,13 @@ __global__ void skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int 
                                  int crop_y, int crop_x, uint4* __restrict__ dZ) {
   constexpr int S = WINDOWED ? 2 : 1;
   const int Hw = H / S, Ww = W / S;
-  const long long total = 1LL * N * Hw * Ww * G;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
-       i += 1LL * gridDim.x * blockDim.x) {
-    const int g = static_cast<int>(i % G);
-    const long long p = i / G;
-    const int wx = static_cast<int>(p % Ww);
-    const int wy = static_cast<int>((p / Ww) % Hw);
-    const int n = static_cast<int>(p / (1LL * Ww * Hw));
+  // grid = (ceil(Ww*G / blockDim), Hw, N): no 64-bit divisions (this kernel was instruction-,
+  // not HBM-bound with a flat grid-stride index)
+  const int wy = blockIdx.y, n = blockIdx.z;
+  const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xg < Ww * G) {
+    const int wx = xg / G, g = xg - wx * G;
+    const long long i = (1LL * n * Hw + wy) * (Ww * G) + xg;
     float yv[S * S][8], gr[S * S][8];
     long long idx[S * S];
 #pragma unroll
@@ -468,7 +511,8 @@ __global__ void relu_mask_kernel(const __nv_bfloat16* __restrict__ Y, long long 
   }
 }
 
-// BiasAddGrad: out[c] += sum over pixels.  blockDim = G * k threads; thread (lane, g).
+// BiasAddGrad: out[c] += sum over pixels.  blockDim = G * k threads; thread (lane, g).  Blocks
+// walk image rows (32-bit index math only), four independent 16-byte loads in flight per thread.
 __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ v, long long sn, long long sy,
                                  long long sx, int N, int H, int W, int G, int k,
                                  float* __restrict__ out) {
@@ -479,27 +523,25 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ v, long long 
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  const long long pixels = 1LL * N * H * W;
-  const long long stride = 1LL * gridDim.x * k;
-  for (long long p0 = blockIdx.x * 1LL * k + lane; p0 < pixels; p0 += 4 * stride) {
-    uint4 raw[4];
+  const int rows = N * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, y = row - n * H;
+    const __nv_bfloat16* __restrict__ base = v + n * sn + y * sy + g * 8;
+    for (int x0 = lane; x0 < W; x0 += 4 * k) {
+      uint4 raw[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {  // four independent 16-byte loads in flight per thread
-      const long long p = p0 + u * stride;
-      raw[u] = make_uint4(0, 0, 0, 0);
-      if (p < pixels) {
-        const int x = static_cast<int>(p % W);
-        const int y = static_cast<int>((p / W) % H);
-        const int n = static_cast<int>(p / (1LL * W * H));
-        raw[u] = __ldg(reinterpret_cast<const uint4*>(v + n * sn + y * sy + x * sx) + g);
+      for (int u = 0; u < 4; ++u) {
+        const int x = x0 + u * k;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (x < W) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + x * sx));
       }
-    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[8];
-      unpack8(raw[u], f);
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
     }
   }
 #pragma unroll
@@ -512,31 +554,38 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ v, long long 
 // weight_output 1x1 conv (unet.py:95) + softmax P(road) (tf_aerial_images.py:147-148) + mean
 // sparse softmax cross-entropy (:103-110) and all gradients that leave this layer.
 // LP = C/8 lanes cooperate on one pixel (each owns 8 channels).
-template <int LP>
-__global__ void __launch_bounds__(256, 3) head_kernel(const uint4* __restrict__ act, long long pixels, const float* __restrict__ w,
-                            const float* __restrict__ b, const unsigned char* __restrict__ labels,
-                            float* __restrict__ probs, float* __restrict__ logits,
-                            float* __restrict__ loss, uint4* __restrict__ dZ, float* __restrict__ dW,
-                            float* __restrict__ db, float inv_count) {
+// Two classes: everything depends on the logit difference d = l1 - l0 only --
+//   P(road) = sigmoid(d),  CE = log(1 + e^-|d|) + (label is the larger logit ? 0 : |d|),
+//   dl1 = (P(road) - label) / count = -dl0,  dZ = dl1 * (w1 - w0),  dW[:,0] = -dW[:,1]
+// -- which halves the arithmetic of this instruction-bound (not yet HBM-bound) kernel.  The
+// separate logits l0, l1 are only evaluated when the caller asks for them (LOGITS).
+template <int LP, bool LOGITS>
+__global__ void __launch_bounds__(256, 3)
+    head_kernel(const uint4* __restrict__ act, long long pixels, const float* __restrict__ w,
+                const float* __restrict__ b, const unsigned char* __restrict__ labels,
+                float* __restrict__ probs, float* __restrict__ logits, float* __restrict__ loss,
+                uint4* __restrict__ dZ, float* __restrict__ dW, float* __restrict__ db,
+                float inv_count) {
   constexpr int PPW = 32 / LP;  // pixels per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane % LP;  // channel group
   const int pw = lane / LP;   // pixel slot in warp
-  float w0[8], w1[8];
+  float w0[LOGITS ? 8 : 1], wd[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    w0[e] = __ldg(w + (sub * 8 + e) * 2 + 0);
-    w1[e] = __ldg(w + (sub * 8 + e) * 2 + 1);
+    const float a0 = __ldg(w + (sub * 8 + e) * 2 + 0), a1 = __ldg(w + (sub * 8 + e) * 2 + 1);
+    if (LOGITS) w0[e] = a0;
+    wd[e] = a1 - a0;
   }
-  const float b0 = __ldg(b), b1 = __ldg(b + 1);
-  float aw0[8], aw1[8], ab0 = 0.f, ab1 = 0.f, aloss = 0.f;
+  const float b0 = __ldg(b), bd = __ldg(b + 1) - b0;
+  float aw1[8], ab1 = 0.f, aloss = 0.f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) aw0[e] = aw1[e] = 0.f;
+  for (int e = 0; e < 8; ++e) aw1[e] = 0.f;
 
   const long long warp_global = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = (1LL * gridDim.x * blockDim.x) >> 5;
   // U pixel groups per iteration: all activation (and label) loads are issued before the first
-  // dependent instruction, which is what keeps enough bytes in flight for this HBM-bound kernel
+  // dependent instruction
   constexpr int U = 4;
   for (long long p0 = warp_global * (PPW * U); p0 < pixels; p0 += n_warps * (PPW * U)) {
     uint4 raw[U];
@@ -557,44 +606,40 @@ __global__ void __launch_bounds__(256, 3) head_kernel(const uint4* __restrict__ 
       const bool ok = p < pixels;
       float a[8];
       unpack8(raw[u], a);
-      float l0 = 0.f, l1 = 0.f;
+      float d = 0.f, l0 = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        l0 += a[e] * w0[e];
-        l1 += a[e] * w1[e];
+        d += a[e] * wd[e];
+        if (LOGITS) l0 += a[e] * w0[e];
       }
 #pragma unroll
       for (int o = LP / 2; o > 0; o >>= 1) {
-        l0 += __shfl_xor_sync(0xffffffffu, l0, o);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (LOGITS) l0 += __shfl_xor_sync(0xffffffffu, l0, o);
       }
-      l0 += b0;
-      l1 += b1;
-      const float mx = fmaxf(l0, l1);
-      const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx);
-      const float inv = 1.f / (e0 + e1);
-      const float p1 = e1 * inv;
+      d += bd;
+      const float ad = fabsf(d);
+      const float en = __expf(-ad);         // e^-|d|  (softmax numerator of the smaller logit)
+      const float inv = 1.f / (1.f + en);
+      const float p1 = d >= 0.f ? inv : en * inv;
       if (ok && sub == 0) {
         if (probs) probs[p] = p1;
-        if (logits) {
-          logits[p * 2] = l0;
-          logits[p * 2 + 1] = l1;
+        if (LOGITS) {
+          logits[p * 2] = l0 + b0;
+          logits[p * 2 + 1] = l0 + b0 + d;
         }
       }
       if (labels != nullptr && ok) {
         const float dl1 = (p1 - (lab[u] ? 1.f : 0.f)) * inv_count;
-        const float dl0 = -dl1;  // (p0 - onehot0) = -(p1 - onehot1)
         if (sub == 0) {
-          aloss += (mx + __logf(e0 + e1)) - (lab[u] ? l1 : l0);
-          ab0 += dl0;
+          aloss += __logf(1.f + en) + (((d >= 0.f) == (lab[u] != 0)) ? 0.f : ad);
           ab1 += dl1;
         }
         float gz[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          aw0[e] += a[e] * dl0;
           aw1[e] += a[e] * dl1;
-          gz[e] = a[e] > 0.f ? dl0 * w0[e] + dl1 * w1[e] : 0.f;
+          gz[e] = a[e] > 0.f ? dl1 * wd[e] : 0.f;
         }
         dZ[p * LP + sub] = pack8(gz);
       }
@@ -602,43 +647,38 @@ __global__ void __launch_bounds__(256, 3) head_kernel(const uint4* __restrict__ 
   }
   if (labels == nullptr) return;
   // reduce across pixel slots of the warp, then across warps through shared memory
-  __shared__ float s_w[LP * 16];
-  __shared__ float s_s[3];
-  for (int j = threadIdx.x; j < LP * 16; j += blockDim.x) s_w[j] = 0.f;
-  if (threadIdx.x < 3) s_s[threadIdx.x] = 0.f;
+  __shared__ float s_w[LP * 8];
+  __shared__ float s_s[2];
+  for (int j = threadIdx.x; j < LP * 8; j += blockDim.x) s_w[j] = 0.f;
+  if (threadIdx.x < 2) s_s[threadIdx.x] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
 #pragma unroll
-    for (int o = LP; o < 32; o <<= 1) {
-      aw0[e] += __shfl_xor_sync(0xffffffffu, aw0[e], o);
-      aw1[e] += __shfl_xor_sync(0xffffffffu, aw1[e], o);
-    }
+    for (int o = LP; o < 32; o <<= 1) aw1[e] += __shfl_xor_sync(0xffffffffu, aw1[e], o);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     aloss += __shfl_xor_sync(0xffffffffu, aloss, o);
-    ab0 += __shfl_xor_sync(0xffffffffu, ab0, o);
     ab1 += __shfl_xor_sync(0xffffffffu, ab1, o);
   }
   if (pw == 0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&s_w[(sub * 8 + e) * 2 + 0], aw0[e]);
-      atomicAdd(&s_w[(sub * 8 + e) * 2 + 1], aw1[e]);
-    }
+    for (int e = 0; e < 8; ++e) atomicAdd(&s_w[sub * 8 + e], aw1[e]);
   }
   if (lane == 0) {
     atomicAdd(&s_s[0], aloss);
-    atomicAdd(&s_s[1], ab0);
-    atomicAdd(&s_s[2], ab1);
+    atomicAdd(&s_s[1], ab1);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < LP * 16; j += blockDim.x) atomicAdd(dW + j, s_w[j]);
+  for (int j = threadIdx.x; j < LP * 8; j += blockDim.x) {
+    atomicAdd(dW + 2 * j + 1, s_w[j]);
+    atomicAdd(dW + 2 * j, -s_w[j]);
+  }
   if (threadIdx.x == 0) {
     atomicAdd(loss, s_s[0] * inv_count);
-    atomicAdd(db, s_s[1]);
-    atomicAdd(db + 1, s_s[2]);
+    atomicAdd(db, -s_s[1]);
+    atomicAdd(db + 1, s_s[1]);
   }
 }
 
@@ -781,10 +821,10 @@ int rsu_pack_plan(const rsu_pack_job* jobs_host, int n_jobs, void* table_dev, in
     d.ld = h.ld > 0 ? h.ld : h.T * h.R;
     d.block_begin = blocks;
     if (h.kind == 0) {
-      d.block_count = h.T * ((h.R + 31) / 32) * ((h.C + 31) / 32);
+      d.block_count = h.T * ((h.R + 63) / 64) * ((h.C + 31) / 32);
     } else {
       const long long total = 1LL * h.T * h.R * h.C;
-      long long b = (total + 256 * 16 - 1) / (256 * 16);  // 16 elements per thread
+      long long b = (total + 256 * 32 - 1) / (256 * 32);  // 32 elements (4 vector groups) per thread
       d.block_count = static_cast<int>(b < 1 ? 1 : b);
     }
     blocks += d.block_count;
@@ -843,12 +883,13 @@ int rsu_skip_grad(const void* Y, int N, int H, int W, int C, const void* dP, con
       dCrop ? static_cast<const __nv_bfloat16*>(dCrop->ptr) : nullptr, dCrop ? dCrop->sn : 0,    \
       dCrop ? dCrop->sy : 0, dCrop ? dCrop->sx : 0, dCrop ? dCrop->H : 0, dCrop ? dCrop->W : 0,  \
       crop_y, crop_x, static_cast<uint4*>(dZ)
+  if (N > 65535 || H > 65535) return set_error(RSU_EINVAL, "skip_grad: N or H > 65535");
   if (dP) {
-    const long long total = 1LL * N * (H / 2) * (W / 2) * (C / 8);
-    skip_grad_kernel<true><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
+    const dim3 grid(((W / 2) * (C / 8) + 127) / 128, H / 2, N);
+    skip_grad_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
   } else {
-    const long long total = 1LL * N * H * W * (C / 8);
-    skip_grad_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
+    const dim3 grid((W * (C / 8) + 255) / 256, H, N);
+    skip_grad_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
   }
 #undef RSU_SKIP_ARGS
   return check_launch("skip_grad");
@@ -875,9 +916,9 @@ int rsu_bias_grad(const rsu_view* v, float* out, void* stream) {
   const int G = v->C / 8;
   int k = 256 / G;
   if (k < 1) k = 1;
-  const long long pixels = 1LL * v->N * v->H * v->W;
-  long long blocks = (pixels + k - 1) / k;
-  const long long cap = 1LL * num_sms() * 6;
+  if (1LL * v->N * v->H > 0x7fffffffLL) return set_error(RSU_EINVAL, "bias_grad: too many rows");
+  long long blocks = 1LL * v->N * v->H;
+  const long long cap = 1LL * num_sms() * 8;
   if (blocks > cap) blocks = cap;
   bias_grad_kernel<<<static_cast<int>(blocks), G * k, G * 8 * sizeof(float), (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(v->ptr), v->sn, v->sy, v->sx, v->N, v->H, v->W, G, k, out);
@@ -893,11 +934,18 @@ int rsu_head(const void* act, int N, int H, int W, int C, const float* w, const 
   const float inv_count = 1.0f / static_cast<float>(pixels);
   const int threads = 256;
   int grid = grid_for(pixels * (C / 8), threads);
-  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  if (grid > num_sms() * 6) grid = num_sms() * 6;  // 3 resident blocks per SM (80 registers): two full rounds
 #define RSU_HEAD(LP)                                                                         \
-  head_kernel<LP><<<grid, threads, 0, (cudaStream_t)stream>>>(                               \
-      static_cast<const uint4*>(act), pixels, w, b, labels, probs, logits, loss,            \
-      static_cast<uint4*>(dZ), dW, db, inv_count)
+  do {                                                                                       \
+    if (logits)                                                                              \
+      head_kernel<LP, true><<<grid, threads, 0, (cudaStream_t)stream>>>(                     \
+          static_cast<const uint4*>(act), pixels, w, b, labels, probs, logits, loss,        \
+          static_cast<uint4*>(dZ), dW, db, inv_count);                                      \
+    else                                                                                     \
+      head_kernel<LP, false><<<grid, threads, 0, (cudaStream_t)stream>>>(                    \
+          static_cast<const uint4*>(act), pixels, w, b, labels, probs, logits, loss,        \
+          static_cast<uint4*>(dZ), dW, db, inv_count);                                      \
+  } while (0)
   if (C == 64) RSU_HEAD(8);
   else if (C == 128) RSU_HEAD(16);
   else if (C == 256) RSU_HEAD(32);

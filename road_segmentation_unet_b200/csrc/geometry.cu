@@ -252,15 +252,19 @@ __global__ void __launch_bounds__(128)
 }
 
 // images.images_from_patches (images.py:131-164) in gather form: every output pixel sums the
-// patches covering it in the reference's order (x outer, y inner) in fp64 and divides by the
-// hit count -- deterministic, no atomics.  Eight loads of the inner loop are issued together.
+// patches covering it in fp64 and divides by the hit count -- deterministic, no atomics.  A
+// pixel is covered by up to (P/stride)^2 patches (1,089 at P = 388, stride 12), far too long a
+// chain of dependent loads for one thread, so the 8 thread rows of a block each take every 8th
+// patch column (kx), issue eight loads of the inner (ky) loop together, and the 8 partial sums
+// are combined in a fixed order through shared memory.
 // k_lo/k_hi restrict the sum to patches whose global index (n*side*side + k) lies in
 // [k_lo, k_hi) -- a rank of a sharded prediction holds only that slice (patches points at patch
 // k_lo) and emits partial sums (normalize = 0) that are added and divided after the gather.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     overlap_average_kernel(const float* __restrict__ patches, int side, int P, int C, int stride,
                            int S, long long k_lo, long long k_hi, int normalize,
                            float* __restrict__ out) {
+  __shared__ double part[8][32];
   const int row = blockIdx.x;  // n*S + y
   const int n = row / S, y = row - n * S;
   const int row_elems = S * C;
@@ -269,32 +273,43 @@ __global__ void __launch_bounds__(128)
   if (y - P + 1 <= 0) ky_lo = 0;
   const int ky_hi = min(y / stride, side - 1);
   const long long img_k0 = 1LL * n * side * side;
+  const long long ky_step = patch_elems - 1LL * stride * P * C;  // next ky: next patch, stride rows up
   constexpr int U = 8;
-  for (int xc = blockIdx.y * blockDim.x + threadIdx.x; xc < row_elems; xc += gridDim.y * blockDim.x) {
-    const int x = xc / C, c = xc - x * C;
-    int kx_lo = (x - P + stride) / stride;
+  const int xc = blockIdx.y * 32 + threadIdx.x;
+  const bool ok = xc < row_elems;
+  int kx_lo = 0, kx_hi = -1, x = 0, c = 0;
+  if (ok) {
+    x = xc / C;
+    c = xc - x * C;
+    kx_lo = (x - P + stride) / stride;
     if (x - P + 1 <= 0) kx_lo = 0;
-    const int kx_hi = min(x / stride, side - 1);
-    double acc = 0.0;
-    for (int kx = kx_lo; kx <= kx_hi; ++kx) {
-      const long long kcol = img_k0 + 1LL * kx * side;
-      const float* __restrict__ base = patches + (kcol - k_lo) * patch_elems +
-                                       (1LL * y * P + (x - kx * stride)) * C + c;
-      const long long ky_step = patch_elems - 1LL * stride * P * C;  // next ky: next patch, stride rows up
-      for (int ky0 = ky_lo; ky0 <= ky_hi; ky0 += U) {
-        float v[U];
+    kx_hi = min(x / stride, side - 1);
+  }
+  double acc = 0.0;
+  for (int kx = kx_lo + threadIdx.y; kx <= kx_hi; kx += 8) {
+    const long long kcol = img_k0 + 1LL * kx * side;
+    const float* __restrict__ base =
+        patches + (kcol - k_lo) * patch_elems + (1LL * y * P + (x - kx * stride)) * C + c;
+    for (int ky0 = ky_lo; ky0 <= ky_hi; ky0 += U) {
+      float v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int ky = ky0 + u;
-          const long long k = kcol + ky;
-          v[u] = (ky <= ky_hi && k >= k_lo && k < k_hi) ? __ldg(base + ky * ky_step) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) acc += static_cast<double>(v[u]);
+      for (int u = 0; u < U; ++u) {
+        const int ky = ky0 + u;
+        const long long k = kcol + ky;
+        v[u] = (ky <= ky_hi && k >= k_lo && k < k_hi) ? __ldg(base + ky * ky_step) : 0.f;
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += static_cast<double>(v[u]);
     }
+  }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sum += part[q][threadIdx.x];
     const int cnt = (kx_hi - kx_lo + 1) * (ky_hi - ky_lo + 1);
-    out[1LL * row * row_elems + xc] = static_cast<float>(normalize ? acc / static_cast<double>(cnt) : acc);
+    out[1LL * row * row_elems + xc] = static_cast<float>(normalize ? sum / static_cast<double>(cnt) : sum);
   }
 }
 
@@ -485,10 +500,10 @@ int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int
   const int S = (side - 1) * stride + P;
   const long long rows = 1LL * N * S;
   if (rows > 0x7fffffffLL) return set_error(RSU_EINVAL, "overlap_average: more than 2^31 rows");
-  int gy = (S * C + 127) / 128;
-  if (gy > 65535) gy = 65535;
-  const dim3 grid(static_cast<unsigned>(rows), gy);
-  overlap_average_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(patches, side, P, C, stride, S, k_begin,
+  const int gy = (S * C + 31) / 32;
+  if (gy > 65535) return set_error(RSU_EINVAL, "overlap_average: row too long");
+  const dim3 grid(static_cast<unsigned>(rows), gy), block(32, 8);
+  overlap_average_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(patches, side, P, C, stride, S, k_begin,
                                                                  k_begin + k_count, normalize, out);
   return check_launch("overlap_average");
 }

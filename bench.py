@@ -28,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "U-Net train patches/s (388^2)"
 UNIT = "patches/s"

@@ -187,6 +187,22 @@ int rsu_dropout_mask(float* m, long long n, float keep, unsigned long long seed,
 int rsu_momentum_sgd(float* w, float* acc, const float* g, long long n, float lr, float momentum,
                      float gscale, void* stream);
 
+/* First-layer (Cin = 3) 3x3 convolution with the im2col operand generated on the fly
+ * (color_space_adjust + dropout + conv_0/conv1 or conv_dilut_0/atrous_conv1, src/unet.py:22-23,
+ * 29-30, 34-35, 42-43).  img: fp32 [N,S,S,3]; cw / cb: DEVICE fp32 [3][3] / [3] colour transform
+ * applied to (x - 0.5), or both NULL = identity (the transform folded into the kernel, keep = 1); the window of the
+ * image starting at (oy, ox) is convolved with dilation `dilation`.  w_packed: bf16 [cout][64]
+ * (k = tap*3 + c < 27, zero beyond); out: bf16 view [N,Ho,Wo,cout], cout = 64 or 128. */
+int rsu_first_conv_fwd(const float* img, int N, int S, const float* cw, const float* cb,
+                       int dilation, int oy, int ox, const void* w_packed, const float* bias,
+                       int relu, const rsu_view* out, float keep, unsigned long long seed,
+                       void* stream);
+/* Its weight gradient: dw[k][co] += sum_pixels im2col[pixel][k] * dz[pixel][co] for k < 28 (row 27
+ * is the constant-one column = BiasAddGrad); dw fp32 with row stride ldo, accumulated into. */
+int rsu_first_conv_wgrad(const float* img, int N, int S, const float* cw, const float* cb,
+                         int dilation, int oy, int ox, const rsu_view* dz, float* dw, int ldo,
+                         float keep, unsigned long long seed, void* stream);
+
 /* ---------------------------------------------------------------- geometry (images.py) ---- */
 /* images.mirror_border (images.py:269-281): np.pad(..., "symmetric") on H and W; fp32. */
 int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* out, void* stream);

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "rsu_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "rsu_color_im2col": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _ull, _vp]),
     "rsu_color_im2col_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _ull, _vp]),
+    "rsu_first_conv_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(View), _f, _ull, _vp]),
+    "rsu_first_conv_wgrad": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, C.POINTER(View), _vp, _i, _f, _ull, _vp]),
     "rsu_pack_plan_bytes": (_i, [_i]),
     "rsu_pack_plan": (_i, [C.POINTER(PackJob), _i, _vp, C.POINTER(C.c_int)]),
     "rsu_pack_run": (_i, [_vp, _i, _i, _vp]),

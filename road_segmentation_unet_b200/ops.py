@@ -274,6 +274,30 @@ def color_im2col_bwd(img, dcol, dilation, oy, ox, dw1, db1, keep=1.0, seed=0):
          dcol.shape[2], _ptr(dw1), _ptr(db1), float(keep), int(seed))
 
 
+def first_conv_fwd(img, cw, cb, dilation, oy, ox, w_packed, bias, out, relu=True, keep=1.0, seed=0):
+    """Cin = 3 convolution with the im2col operand built on the fly (rsu_first_conv_fwd): the
+    window of img [N,S,S,3] fp32 at (oy, ox) -> out [N,Ho,Wo,cout] bf16, cout = 64 or 128.
+    cw / cb: device fp32 colour transform applied to (x - 0.5)."""
+    n, s = img.shape[0], img.shape[1]
+    ov = view(out)
+
+    def run(*a):
+        call("rsu_first_conv_fwd", *a)
+    _timed("conv_gemm", run, _ptr(img), n, s, _ptr(cw), _ptr(cb), int(dilation), int(oy), int(ox),
+           _ptr(w_packed), _ptr(bias), int(relu), C.byref(ov), float(keep), int(seed))
+
+
+def first_conv_wgrad(img, cw, cb, dilation, oy, ox, dz, dw, keep=1.0, seed=0):
+    """dw[k, co] += im2col(img)^T dz for k < 28 (row 27 = BiasAddGrad); dw fp32 [>= 28, cout]."""
+    n, s = img.shape[0], img.shape[1]
+    gv = view(dz)
+
+    def run(*a):
+        call("rsu_first_conv_wgrad", *a)
+    _timed("wgrad_gemm", run, _ptr(img), n, s, _ptr(cw), _ptr(cb), int(dilation), int(oy), int(ox),
+           C.byref(gv), _ptr(dw), int(dw.stride(0)), float(keep), int(seed))
+
+
 def first_layer_fold(w, b, w1, b1, w_packed, bias_eff):
     """Fold color_space_adjust into a Cin = 3 convolution (w: HWIO fp32 [3,3,3,cout])."""
     call("rsu_first_layer_fold", _ptr(w), _ptr(b), _ptr(w1), _ptr(b1), w.shape[3], _ptr(w_packed),

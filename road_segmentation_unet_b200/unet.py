@@ -262,10 +262,14 @@ class UNet:
                 self.dD1.append(None)
                 self.dD2.append(None)
         # first layer im2col buffers (Cin = 3 -> 64 padded channels)
+        # (root 64 / 128: the Cin = 3 layers build their im2col operand inside the kernel,
+        # rsu_first_conv_*, and no im2col tensor exists)
         s0 = self.in_size[0]
-        self.col = self._bf(B, s0 - 2, s0 - 2, 64)
+        # (TMA over the fp32 image rows needs 16-byte row strides: S % 4 == 0)
+        self.fused_first = f[0] in (64, 128) and s0 % 4 == 0 and self.P >= 16
+        self.col = None if self.fused_first else self._bf(B, s0 - 2, s0 - 2, 64)
         self.dcol = None  # gradient of the im2col matrix: only the dropout path needs it (lazy)
-        if self.dilated and L > 1:
+        if self.dilated and L > 1 and not self.fused_first:
             t0 = self.up_size[L - 2]
             self.colD = self._bf(B, t0 + 4, t0 + 4, 64)
         else:
@@ -380,18 +384,11 @@ class UNet:
                 # matrix holds x - 0.5 (identity transform) and the kernel / bias are W1.W, b + b1.W
                 seed0 = self._site_seed(site)
                 cw, cb = (w1, b1) if drop else (self._eye3, self._zero3)
-                ops.color_im2col(images, cw, cb, 1, 0, 0, self.col, keep, seed0)
-                self._tag(reg1.name)
-                ops.conv_gemm([(self.col, 0, 0)], [(0, 0)], reg1.w_fwd if drop else reg1.w_fold,
-                              self.A1[0], f[0], bias=bias(reg1.name) if drop else reg1.bias_fold,
-                              relu=True)
+                self._first_fwd(reg1, images, cw, cb, 1, 0, 0, self.col, self.A1[0], drop, keep, seed0)
                 if dil_live:
                     d1 = self.convs["conv_dilut_0/atrous_conv1"]
-                    ops.color_im2col(images, cw, cb, 2, o2, o2, self.colD, keep, seed0)
-                    self._tag(d1.name)
-                    ops.conv_gemm([(self.colD, 0, 0)], [(0, 0)], d1.w_fwd if drop else d1.w_fold,
-                                  self.D1[0], f[0], bias=bias(d1.name) if drop else d1.bias_fold,
-                                  relu=True)
+                    self._first_fwd(d1, images, cw, cb, 2, o2, o2, self.colD, self.D1[0], drop, keep,
+                                    seed0)
             else:
                 src = self.Pool[i - 1]
                 if drop:
@@ -456,6 +453,19 @@ class UNet:
                      db=self.var("weight_output/bias", "grads"))
         return self.probs
 
+    def _first_fwd(self, conv, images, cw, cb, dilation, oy, ox, col, out, drop, keep, seed):
+        """Cin = 3 convolution: im2col built inside the kernel (root 64 / 128), else through a
+        materialised im2col tensor and the generic implicit GEMM."""
+        w = conv.w_fwd if drop else conv.w_fold
+        b = self.var(conv.name + "/bias") if drop else conv.bias_fold
+        self._tag(conv.name)
+        if self.fused_first:
+            ops.first_conv_fwd(images, cw if drop else None, cb if drop else None, dilation, oy, ox, w, b,
+                               out, relu=True, keep=keep, seed=seed)
+        else:
+            ops.color_im2col(images, cw, cb, dilation, oy, ox, col, keep, seed)
+            ops.conv_gemm([(col, 0, 0)], [(0, 0)], w, out, out.shape[3], bias=b, relu=True)
+
     # ------------------------------------------------------------------ backward
     def _tag(self, name):
         ops.set_layer(name, self._flops.get(name, 0.0))
@@ -476,7 +486,14 @@ class UNet:
         self._tag(conv.name)
         g = lambda n: self.var(conv.name + "/" + n, "grads")
         conv.dw_stage.zero_()
-        ops.wgrad_gemm([(col, 0, 0)], [(0, 0)], dz, (0, 0), conv.dw_stage, (dz.shape[1], dz.shape[2]))
+        if self.fused_first:
+            drop = self._keep < 1.0
+            cw = self.var("color_space_adjust/kernel") if drop else None
+            cb = self.var("color_space_adjust/bias") if drop else None
+            ops.first_conv_wgrad(self._images, cw, cb, dilation, oy, ox, dz, conv.dw_stage,
+                                 keep=self._keep, seed=self._site_seed(0))
+        else:
+            ops.wgrad_gemm([(col, 0, 0)], [(0, 0)], dz, (0, 0), conv.dw_stage, (dz.shape[1], dz.shape[2]))
         if self._keep >= 1.0:
             # folded layer: everything follows from the 28 x Cout matrix im2col(x - 0.5)^T dZ
             # (row 27, the constant-one column, is the bias gradient)
@@ -489,7 +506,7 @@ class UNet:
         g("kernel").view(27, conv.cout).add_(conv.dw_stage[:27])
         g("bias").add_(conv.dw_stage[27])
         if getattr(self, which_dcol) is None:
-            setattr(self, which_dcol, torch.empty_like(col))
+            setattr(self, which_dcol, self._bf(dz.shape[0], dz.shape[1], dz.shape[2], 64))
         dcol = getattr(self, which_dcol)
         ops.conv_gemm([(dz, 0, 0)], [(0, 0)], conv.w_dgrad, dcol, 64)
         ops.color_im2col_bwd(self._images, dcol, dilation, oy, ox,

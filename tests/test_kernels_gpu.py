@@ -394,6 +394,63 @@ def test_first_layer_fold_and_grads(ops):
     assert rel_err(db1.cpu().numpy(), tb1.grad.numpy()) < 1e-2
 
 
+FIRST_CASES = [
+    # (N, S, cout, dilation, oy, ox, Ho, keep)
+    (2, 40, 64, 1, 0, 0, 38, 1.0),     # whole image, ragged 38 x 38 output (tiles 8 x 16)
+    (1, 60, 64, 2, 6, 6, 44, 1.0),     # dilated window at an offset (the cropped dilated branch)
+    (2, 36, 128, 1, 0, 0, 34, 1.0),    # root 128: two 64-channel column blocks
+    (1, 52, 64, 1, 3, 1, 30, 0.8),     # colour transform + dropout inside the producer
+]
+
+
+@pytest.mark.parametrize("case", FIRST_CASES)
+def test_first_conv_fused(ops, case):
+    """Cin = 3 convolution and weight gradient with the im2col operand built inside the kernel
+    (rsu_first_conv_fwd / rsu_first_conv_wgrad) against fp64 torch-CPU arithmetic on the same
+    bf16-rounded operands (unet.py:22-23, 29-30, 34-35, 42-43)."""
+    n, s, cout, d, oy, ox, ho, keep = case
+    rs = np.random.RandomState(17)
+    img = rs.rand(n, s, s, 3).astype(np.float32)
+    if keep < 1.0:
+        w1 = (np.eye(3) + 0.3 * rs.randn(3, 3)).astype(np.float32)
+        b1 = (0.2 * rs.randn(3)).astype(np.float32)
+    else:
+        w1, b1 = np.eye(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+    w = bf((rs.randn(3, 3, 3, cout) / np.sqrt(27)).astype(np.float32))
+    b = rs.randn(cout).astype(np.float32)
+    seed = 91
+    scales = np.ones((n, s, s, 3), dtype=np.float32)
+    if keep < 1.0:
+        scales = ops.dropout_mask(n * s * s * 3, keep, seed).cpu().numpy().reshape(n, s, s, 3)
+    net0 = bf((((img - 0.5) @ w1 + b1) * scales).astype(np.float32))  # what the producer rounds to bf16
+    win = net0[:, oy:oy + ho + 2 * d, ox:ox + ho + 2 * d]
+    ref = torch.relu(O.conv2d_valid(torch.tensor(win, dtype=torch.float64), torch.tensor(w, dtype=torch.float64),
+                                    torch.tensor(b, dtype=torch.float64), dilation=d)).numpy()
+    wp = torch.zeros(cout, 64, dtype=torch.bfloat16, device="cuda")
+    ops.pack_conv_fwd(dev(w, torch.float32), wp, 1, 27, cout, ld=64)
+    out = torch.full((n, ho, ho, cout), -5.0, dtype=torch.bfloat16, device="cuda")
+    d_img = dev(img, torch.float32)
+    # keep == 1: identity transform passed as None (the folded-layer fast path of the producers)
+    d_w1, d_b1 = (dev(w1, torch.float32), dev(b1, torch.float32)) if keep < 1.0 else (None, None)
+    ops.first_conv_fwd(d_img, d_w1, d_b1, d, oy, ox, wp, dev(b, torch.float32), out, relu=True,
+                       keep=keep, seed=seed)
+    assert rel_err(out.float().cpu().numpy(), ref) < 6e-3
+    # weight gradient: rows k = tap*3 + c (k < 27), row 27 = column sums of dZ
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    col = np.zeros((n, ho, ho, 28), dtype=np.float64)
+    for t in range(9):
+        ky, kx = divmod(t, 3)
+        col[..., t * 3:t * 3 + 3] = win[:, ky * d:ky * d + ho, kx * d:kx * d + ho]
+    col[..., 27] = 1.0
+    ref_g = np.einsum("nhwk,nhwc->kc", col, dz.astype(np.float64))
+    g = torch.zeros(64, cout, dtype=torch.float32, device="cuda")
+    g[:28] = 1.5  # accumulated into, rows >= 28 untouched
+    ops.first_conv_wgrad(d_img, d_w1, d_b1, d, oy, ox, dev(dz), g, keep=keep, seed=seed)
+    gh = g.cpu().numpy()
+    assert rel_err(gh[:28] - 1.5, ref_g) < 6e-3
+    assert np.abs(gh[28:]).max() == 0
+
+
 # ------------------------------------------------------------------ halo-tile kernels (algo = 2)
 HALO_FWD_CASES = [
     # (N, H, srcs [(extent, channels, crop)], Cout, dilation)

@@ -355,6 +355,30 @@ def run_gpu(args):
             "other_kernels_ms_per_step": ms_per_step - (conv[1] + wg[1]) / kp,
         }
 
+    # ---- HBM-bound kernels of the path (geometry helpers, head, pool, SGD): achieved GB/s against
+    # the measured copy bandwidth (north_star item 3); single GPU, rank 0 only, no collectives
+    hbm = None
+    if rank == 0 and not args.no_hbm:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_hbm
+            res = bench_hbm.run()
+            hbm = {"peak_gbs": res["peak_gbs"], "peak_source": res["peak_source"],
+                   "kernels": {r["kernel"]: {"gbs": round(r["gbs"], 1), "frac": round(r["frac"], 3),
+                                             "ms": round(r["ms"], 4), "alg_bytes": r["alg_bytes"]}
+                               for r in res["kernels"]}}
+        except Exception as e:  # the headline numbers above must survive a failure here
+            hbm = {"error": repr(e)}
+    # DRAM traffic of the dominant kernel class per step, from the committed ncu pass
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
+    if rank == 0 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
+        if roof is not None:
+            roof["traffic"] = traffic.get("conv_class_dram_bytes_per_step")
+            roof["traffic_source"] = traffic.get("source")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, sec, threads = time_oracle(2, 1)
@@ -377,7 +401,7 @@ def run_gpu(args):
                     "steps": ke, "api": "tf_aerial_images.ConvolutionalModel.train_batch (pinned host batch in, "
                                         "loss + probabilities read back every step)"},
             "gpu_launches": launches, "loss": loss_val, "clocks": clocks,
-            "roofline": roof, "cpu_baseline": cpu, "predict": predict,
+            "roofline": roof, "cpu_baseline": cpu, "predict": predict, "hbm_kernels": hbm,
         }
         line.update(extra)
         print(json.dumps(line))
@@ -396,6 +420,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--quick", action="store_true", help="device-timed region only (for ncu runs)")
     ap.add_argument("--no-predict", action="store_true", help="skip the sliding-window prediction leg")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernel table")
     ap.add_argument("--predict-images", type=int, default=1, help="604^2 images in the prediction leg")
     ap.add_argument("--dump-layers", default="", help="write the per-layer tcgen05 kernel timing table here")
     args = ap.parse_args()

@@ -438,19 +438,38 @@ __global__ void skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int 
   if (xg < Ww * G) {
     const int wx = xg / G, g = xg - wx * G;
     const long long i = (1LL * n * Hw + wy) * (Ww * G) + xg;
-    float yv[S * S][8], gr[S * S][8];
+    // all loads first (Y, pool gradient, cropped concat gradient: up to nine 16-byte loads in
+    // flight per thread), then the arithmetic; out-of-crop pixels re-read their own Y vector (an
+    // L1 hit) instead of branching around the load
     long long idx[S * S];
+    uint4 yraw[S * S], craw[S * S];
+    bool in_crop[S * S];
 #pragma unroll
     for (int q = 0; q < S * S; ++q) {
       const int y = wy * S + q / S, x = wx * S + q % S;
       idx[q] = ((1LL * n * H + y) * W + x) * G + g;
-      unpack8(__ldg(Y + idx[q]), yv[q]);
+      yraw[q] = __ldg(Y + idx[q]);
+    }
+    uint4 praw = make_uint4(0, 0, 0, 0);
+    if (WINDOWED && dP != nullptr) praw = __ldg(dP + i);  // dP is [N, H/2, W/2, C]: same linear index as the window
+#pragma unroll
+    for (int q = 0; q < S * S; ++q) {
+      const int cy = wy * S + q / S - crop_y, cx = wx * S + q % S - crop_x;
+      in_crop[q] = dC != nullptr && cy >= 0 && cy < Hc && cx >= 0 && cx < Wc;
+      const uint4* cp = in_crop[q] ? reinterpret_cast<const uint4*>(dC + n * c_sn + cy * c_sy + cx * c_sx) + g
+                                   : Y + idx[q];
+      craw[q] = __ldg(cp);
+    }
+    float yv[S * S][8], gr[S * S][8];
+#pragma unroll
+    for (int q = 0; q < S * S; ++q) {
+      unpack8(yraw[q], yv[q]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) gr[q][e] = 0.f;
     }
     if (WINDOWED && dP != nullptr) {
       float dp[8];
-      unpack8(__ldg(dP + i), dp);  // dP is [N, H/2, W/2, C]: same linear index as the window
+      unpack8(praw, dp);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         int arg = 0;
@@ -466,16 +485,13 @@ __global__ void skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int 
           if (arg == q) gr[q][e] = dp[e];
       }
     }
-    if (dC != nullptr) {
 #pragma unroll
-      for (int q = 0; q < S * S; ++q) {
-        const int cy = wy * S + q / S - crop_y, cx = wx * S + q % S - crop_x;
-        if (cy >= 0 && cy < Hc && cx >= 0 && cx < Wc) {
-          float dc[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(dC + n * c_sn + cy * c_sy + cx * c_sx) + g), dc);
+    for (int q = 0; q < S * S; ++q) {
+      if (in_crop[q]) {
+        float dc[8];
+        unpack8(craw[q], dc);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) gr[q][e] += dc[e];
-        }
+        for (int e = 0; e < 8; ++e) gr[q][e] += dc[e];
       }
     }
 #pragma unroll

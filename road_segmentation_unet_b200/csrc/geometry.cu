@@ -288,18 +288,21 @@ __global__ void __launch_bounds__(256)
   double acc = 0.0;
   for (int kx = kx_lo + threadIdx.y; kx <= kx_hi; kx += 8) {
     const long long kcol = img_k0 + 1LL * kx * side;
+    // patch rows of this column that are both geometrically covering and in this rank's slice
+    const int lo = static_cast<int>(max(static_cast<long long>(ky_lo), k_lo - kcol));
+    const int hi = static_cast<int>(min(static_cast<long long>(ky_hi), k_hi - 1 - kcol));
+    if (lo > hi) continue;
     const float* __restrict__ base =
         patches + (kcol - k_lo) * patch_elems + (1LL * y * P + (x - kx * stride)) * C + c;
-    for (int ky0 = ky_lo; ky0 <= ky_hi; ky0 += U) {
+    for (int ky0 = lo; ky0 <= hi; ky0 += U) {
+      // eight unconditional loads (indices past the end are clamped and their values dropped)
+      // so that they issue back to back: one memory latency per eight patches
       float v[U];
+      const float* __restrict__ ptr = base + ky0 * ky_step;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ky = ky0 + u;
-        const long long k = kcol + ky;
-        v[u] = (ky <= ky_hi && k >= k_lo && k < k_hi) ? __ldg(base + ky * ky_step) : 0.f;
-      }
+      for (int u = 0; u < U; ++u) v[u] = __ldg(ptr + min(u, hi - ky0) * ky_step);
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc += static_cast<double>(v[u]);
+      for (int u = 0; u < U; ++u) acc += (ky0 + u <= hi) ? static_cast<double>(v[u]) : 0.0;
     }
   }
   part[threadIdx.y][threadIdx.x] = acc;

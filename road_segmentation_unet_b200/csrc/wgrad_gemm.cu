@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 2);  // the A-operand and the B-operand producer warp
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -104,9 +104,13 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     *pt_end = static_cast<int>(1LL * pix_tiles * (ks + 1) / p.ksplit);
   };
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0 || warp == 3) {
+    // ------------------------------------------------------------ TMA producers
+    // warp 0 loads the (up to) two A atoms of a stage, warp 3 its BN/64 B atoms: one warp issuing
+    // all six boxes of a 64-pixel stage was busy three quarters of the time (ncu stall samples)
+    // and could not run far enough ahead of the MMAs.  Each warp posts its own expect_tx.
     // (whole warp converged, one elected lane issues; see conv_gemm.cu)
+    const bool is_a = warp == 0;
     uint32_t stage = 0, phase = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       int m_tile, n_tile, pt0, pt1;
@@ -116,7 +120,8 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       const AtomCoord a0 = decode_atom(p, atom0, chunks_total);
       const AtomCoord a1 = decode_atom(p, n_a == 2 ? atom0 + 1 : atom0, chunks_total);
       const int n0 = n_tile * p.BN;
-      const uint32_t tx_bytes = static_cast<uint32_t>(n_a + n_b_atoms) * box_bytes;
+      const uint32_t tx_bytes = static_cast<uint32_t>(is_a ? n_a : n_b_atoms) * box_bytes;
+      const int bx = p.b_off_x, by = p.b_off_y;
       int img = pt0 / tiles_per_img;
       int r = pt0 % tiles_per_img;
       int ty = r / p.tiles_x, tx = r % p.tiles_x;
@@ -127,13 +132,15 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           const uint32_t dst = smem_base + stage * stage_bytes;
           const uint32_t fb = full_bar(stage);
           mbar_expect_tx(fb, tx_bytes);
-          tma_load_4d(dst, &p.a_map[a0.src], fb, a0.chunk * 64, x0 + a0.dx, y0 + a0.dy, img);
-          if (n_a == 2)
-            tma_load_4d(dst + atom_bytes, &p.a_map[a1.src], fb, a1.chunk * 64, x0 + a1.dx, y0 + a1.dy,
-                        img);
-          for (int j = 0; j < n_b_atoms; ++j)
-            tma_load_4d(dst + (2 + j) * atom_bytes, &p.b_map, fb, n0 + j * 64, x0 + p.b_off_x,
-                        y0 + p.b_off_y, img);
+          if (is_a) {
+            tma_load_4d(dst, &p.a_map[a0.src], fb, a0.chunk * 64, x0 + a0.dx, y0 + a0.dy, img);
+            if (n_a == 2)
+              tma_load_4d(dst + atom_bytes, &p.a_map[a1.src], fb, a1.chunk * 64, x0 + a1.dx, y0 + a1.dy,
+                          img);
+          } else {
+            for (int j = 0; j < n_b_atoms; ++j)
+              tma_load_4d(dst + (2 + j) * atom_bytes, &p.b_map, fb, n0 + j * 64, x0 + bx, y0 + by, img);
+          }
         }
         __syncwarp();
         if (++stage == static_cast<uint32_t>(stages)) {
@@ -171,11 +178,19 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           const uint32_t a_lo = desc_lo_sw128(a_addr, atom_bytes);
           const uint32_t b_lo = desc_lo_sw128(a_addr + 2 * atom_bytes, atom_bytes);
           const uint32_t first = pt != pt0 ? 1u : 0u;
+          // 16 pixels (K) per instruction = 16 rows of 128 B = 2 KiB further into every atom.
+          // (separate loops per tile size: predicated-off tcgen05.mma still take a slot of the
+          // instruction queue, and the 64-pixel stage is issue-paced)
+          if (mma_per_tile == 4) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // 16 pixels (K) per instruction = 16 rows of 128 B = 2 KiB further into every atom
-            if (j < mma_per_tile)
+            for (int j = 0; j < 4; ++j)
               umma_bf16_lohi(d_tmem, a_lo + j * 128u, hi, b_lo + j * 128u, hi, idesc, j != 0 ? 1u : first);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < mma_per_tile)
+                umma_bf16_lohi(d_tmem, a_lo + j * 128u, hi, b_lo + j * 128u, hi, idesc, j != 0 ? 1u : first);
+            }
           }
           umma_commit(empty_bar(stage));
         }
@@ -229,12 +244,12 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 
 int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_done);  // wgrad_halo.cu
 
-// pixels per K step of the per-tap kernel (RSU_WGRAD_TILE = 64 | 128 overrides, for A/B runs)
+// pixels per K step of the per-tap kernel (RSU_WGRAD_TILE = 32 | 64 | 128 overrides, for A/B runs)
 static int wgrad_tile_pixels() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("RSU_WGRAD_TILE");
-    v = (e && atoi(e) == 128) ? 128 : 64;
+    v = (e && atoi(e) == 128) ? 128 : ((e && atoi(e) == 32) ? 32 : 64);
   }
   return v;
 }

@@ -184,10 +184,16 @@ class ConvolutionalModel:
                               self.input_size, seed=opts.seed, training=True)
         B, S, P = opts.batch_size, self.input_size, opts.patch_size
         assert self._net.P == P
-        self._h_patches = torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32).pin_memory()
-        self._h_labels = torch.empty(B, P, P, dtype=torch.uint8).pin_memory()
-        self._d_patches = torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32, device="cuda")
-        self._d_labels = torch.empty(B, P, P, dtype=torch.uint8, device="cuda")
+        # two input slots: while a step computes from one, the next batch is staged (pinned host
+        # copy + host->device transfer on a copy stream) into the other -- see prefetch()
+        self._h_slots = [(torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32).pin_memory(),
+                          torch.empty(B, P, P, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        self._d_slots = [(torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32, device="cuda"),
+                          torch.empty(B, P, P, dtype=torch.uint8, device="cuda")) for _ in range(2)]
+        self._slot = 0
+        self._staged = {}  # id(patches object) -> (patches, labels, slot, ready event)
+        self._slot_free = [None, None]  # event: the last step that read the slot has consumed it
+        self._copy_stream = torch.cuda.Stream()
         self._h_probs = torch.empty(B, P, P, dtype=torch.float32).pin_memory()
         self._reducer = GradientAllReducer(self._dist.dist, self._dist.world, self._net.grads) \
             if self._dist.active else None
@@ -216,26 +222,71 @@ class ConvolutionalModel:
         return images.d4_transform_dev(imgs, ops_t), images.d4_transform_dev(masks, ops_t)
 
     # -- one training step on host batches ---------------------------------------------------
+    def _stage(self, patches_batch, labels_batch, slot, stream):
+        """host batch -> device slot `slot` on `stream` (asynchronous for pinned sources)."""
+        dx, dy = self._d_slots[slot]
+        if torch.is_tensor(patches_batch) and patches_batch.is_pinned():
+            # caller already staged the batch in pinned host memory (fp32 patches, uint8 labels)
+            hx, hy = patches_batch, labels_batch
+        else:
+            hx, hy = self._h_slots[slot]
+            hx.copy_(torch.from_numpy(np.ascontiguousarray(patches_batch, dtype=np.float32)))
+            hy.copy_(torch.from_numpy(np.ascontiguousarray(labels_batch).astype(np.uint8)))
+        with torch.cuda.stream(stream):
+            if self._slot_free[slot] is not None:
+                stream.wait_event(self._slot_free[slot])
+            dx.copy_(hx, non_blocking=True)
+            dy.copy_(hy, non_blocking=True)
+
+    def _free_slot(self):
+        taken = {v[2] for v in self._staged.values()}
+        for slot in (1 - self._slot, self._slot):
+            if slot not in taken:
+                return slot
+        return None
+
+    def prefetch(self, patches_batch, labels_batch):
+        """Start moving a FUTURE batch to the GPU (pinned host copy + transfer on a copy stream)
+        while the current step computes; the train_batch() call with the same patches object picks
+        it up.  Returns False when both input slots are already spoken for.  (The epoch loop of
+        train() and bench.py's end-to-end leg use it; train_batch() alone stays correct.)"""
+        slot = self._free_slot()
+        if slot is None:
+            return False
+        self._stage(patches_batch, labels_batch, slot, self._copy_stream)
+        ev = torch.cuda.Event()
+        ev.record(self._copy_stream)
+        self._staged[id(patches_batch)] = (patches_batch, labels_batch, slot, ev)
+        return True
+
     def train_batch(self, patches_batch, labels_batch):
         """patches_batch [B,S,S,3], labels_batch [B,P,P] (host arrays).  Returns (loss, probs)."""
         opts = self._options
         net = self._net
-        if torch.is_tensor(patches_batch) and patches_batch.is_pinned():
-            # caller already staged the batch in pinned host memory (fp32 patches, uint8 labels)
-            self._d_patches.copy_(patches_batch, non_blocking=True)
-            self._d_labels.copy_(labels_batch, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        st = self._staged.pop(id(patches_batch), None)
+        if st is not None and st[0] is patches_batch:
+            self._slot = st[2]
+            cur.wait_event(st[3])
         else:
-            self._h_patches.copy_(torch.from_numpy(np.ascontiguousarray(patches_batch, dtype=np.float32)))
-            self._h_labels.copy_(torch.from_numpy(np.ascontiguousarray(labels_batch).astype(np.uint8)))
-            self._d_patches.copy_(self._h_patches, non_blocking=True)
-            self._d_labels.copy_(self._h_labels, non_blocking=True)
-        x, y = self._d_patches, self._d_labels
+            slot = self._free_slot()
+            if slot is None:  # both slots hold batches staged for later: drop the older one
+                self._staged.clear()
+                slot = self._slot
+            self._slot = slot
+            self._stage(patches_batch, labels_batch, slot, cur)
+        x, y = self._d_slots[self._slot]
         if opts.image_augmentation:
             x, y = self.stochastic_images_augmentation(x, y)
         lr = net.learning_rate(opts.lr)
         net.grads.zero_()
         net.forward(x, y, keep=opts.dropout)
         net.backward()
+        # (the inputs are read by the forward pass and by the first-layer weight gradient at the
+        # very end of the backward pass: only now may a prefetch overwrite this slot)
+        free = torch.cuda.Event()
+        free.record(cur)
+        self._slot_free[self._slot] = free
         scale = self._reducer.finish() if self._reducer is not None else 1.0
         net.apply_gradients(opts.lr, opts.momentum, scale)
         self._h_probs.copy_(net.probs, non_blocking=True)
@@ -263,9 +314,20 @@ class ConvolutionalModel:
         num_errors = 0
         total = 0
         gb = opts.batch_size * world  # global batch: every rank takes its own slice of it
-        for batch_i, offset in enumerate(range(0, num_train_patches - gb, gb)):
-            batch_indices = rank_batch_indices(indices, offset, rank, opts.batch_size)
-            l, predictions = self.train_batch(patches[batch_indices, :, :, :], labels_patches[batch_indices])
+        offsets = list(range(0, num_train_patches - gb, gb))
+
+        def host_batch(offset):
+            idx = rank_batch_indices(indices, offset, rank, opts.batch_size)
+            return idx, patches[idx, :, :, :], labels_patches[idx]
+
+        nxt = host_batch(offsets[0]) if offsets else None
+        for batch_i, offset in enumerate(offsets):
+            batch_indices, pb, lb = nxt
+            # stage batch i+1 (host gather + pinned copy + transfer) while step i computes
+            nxt = host_batch(offsets[batch_i + 1]) if batch_i + 1 < len(offsets) else None
+            if nxt is not None:
+                self.prefetch(nxt[1], nxt[2])
+            l, predictions = self.train_batch(pb, lb)
             step = self._net.global_step
             print("Batch {} Step {}".format(batch_i, step), end="\r")
 
@@ -313,7 +375,9 @@ class ConvolutionalModel:
         # this rank's contiguous slice of the patch list
         k0, k1 = shard_range(num_patches, rank, world)
         preds = torch.empty(max(k1 - k0, 1), P, P, 1, dtype=torch.float32, device="cuda")
-        batch = self._d_patches
+        if getattr(self, "_d_predict", None) is None:
+            self._d_predict = torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+        batch = self._d_predict
         for k in range(k0, k1, B):
             cnt = min(B, k1 - k)
             # a short tail batch keeps stale patches in the remaining slots (the reference's

@@ -273,8 +273,11 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   // produces the bias gradient, which is counted in its favour)
   int chunks_all = 0;
   for (int s = 0; s < d->n_src && s < kMaxSrc; ++s) chunks_all += d->src[s].C / 64;
+  // (with 128-channel gradient tiles the halo kernel is not shared-memory bound any more, which
+  // also pays for up to 6 input chunks: conv_9/conv1, 384 -> 128 channels)
+  const int max_chunks = (d->grad.C % 128 == 0) ? 6 : 4;
   const bool want_halo =
-      d->algo == 2 || (d->algo == 0 && d->n_taps == 9 && d->H >= 64 && d->W >= 64 && chunks_all <= 4 &&
+      d->algo == 2 || (d->algo == 0 && d->n_taps == 9 && d->H >= 64 && d->W >= 64 && chunks_all <= max_chunks &&
                        (d->grad.C <= 128 || (d->grad.C <= 256 && d->H >= 180)));
   if (want_halo) {
     int bias_done = 0;
@@ -300,8 +303,12 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   // 64-pixel K steps: a stage is (2 + BN/64) x 8 KiB, so four stages fit even at BN = 256 (with
   // 128-pixel steps only two 96 KiB stages did, and the tensor pipe idled ~45 % of the time
   // waiting for loads -- profiles/r1_step_metrics.txt)
+  // ... and at BN <= 128 a 64-pixel stage holds only 4 x 64 cycles of tensor work, less than the
+  // issue loop's own cost per stage (tools/mma_probe.cu): those shapes take 128-pixel stages.
+  const int cout_ = d->grad.C;
+  const int bn_ = cout_ % 256 == 0 ? 256 : (cout_ % 128 == 0 ? 128 : 64);
   int TW, TH;
-  pick_tile(d->W, d->H, max_tw, max_th, true, &TW, &TH, wgrad_tile_pixels());
+  pick_tile(d->W, d->H, max_tw, max_th, true, &TW, &TH, bn_ <= 128 ? 128 : wgrad_tile_pixels());
   if (TW < 1 || TH < 1 || (TW * TH) % 16 != 0)
     return set_error(RSU_EINVAL, "no valid pixel tile for %dx%d (need TW*TH %% 16 == 0)", d->W, d->H);
   p.TW = TW;

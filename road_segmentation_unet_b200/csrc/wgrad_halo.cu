@@ -14,6 +14,13 @@
 // points at a constant block of ones: its rows are the column sums of G, i.e. BiasAddGrad for
 // free.  L2 -> SM traffic per 128 pixels: 22.5 KiB + 16 KiB instead of 9/2 x (32 + 16) KiB.
 //
+//
+// N = 64 instructions are shared-memory-operand bound (48 instead of 32 cycles, tools/mma_probe.cu).
+// When Cout is a multiple of 128 the gradient tile is 128 channels wide instead; five accumulators
+// x 128 columns no longer fit the 512 columns of tensor memory, so the taps are split into two
+// groups -- accumulators {0,1} (taps 0..3) and {2,3,4} (taps 4..8 + ones) -- that are separate
+// units of work (each re-reads the X halo tile and the G tile from L2, which is not the limit).
+//
 // Reference op replaced: Conv2DBackpropFilter + BiasAddGrad of the 3x3 convolutions in
 // src/unet.py:34-45, 88-91.
 #include "gemm_params.h"
@@ -40,6 +47,8 @@ struct WgradHaloParams {
   int Wh, Hh;
   int tiles_x, tiles_y, n_img;
   int chunks_total, n_tiles_n, ksplit;
+  int BN;      // gradient channels per unit: 64 or 128
+  int groups;  // 1: all accumulators in one unit; 2: accumulators {0,1} and {2,3,4} (n_taps == 9)
   int stages;
   uint32_t a_stage_bytes;  // 1024-aligned
   float* out;
@@ -54,7 +63,8 @@ __global__ void __launch_bounds__(kWhThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
-  const uint32_t stage_bytes = p.a_stage_bytes + kWhBBytes;
+  const int n_b_atoms = p.BN / 64;
+  const uint32_t stage_bytes = p.a_stage_bytes + static_cast<uint32_t>(n_b_atoms) * kWhBBytes;
   const uint32_t ones_base = smem_base + stages * stage_bytes;
   const uint32_t bar_base = ones_base + kOnesBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -93,16 +103,22 @@ __global__ void __launch_bounds__(kWhThreads, 1)
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int pix_tiles = p.n_img * tiles_per_img;
-  const int total_units = p.chunks_total * p.n_tiles_n * p.ksplit;
+  const int total_units = p.chunks_total * p.n_tiles_n * p.groups * p.ksplit;
   const int n_mtiles = (p.n_taps + 1) / 2;
   const uint32_t a_bytes = static_cast<uint32_t>(p.Wh * p.Hh) * 128u;
 
-  // unit -> (ks, n_tile, chunk); chunk fastest so that concurrently running CTAs share G and X
-  auto unit_range = [&](int unit, int* cg, int* n_tile, int* pt_begin, int* pt_end) {
+  // unit -> (ks, tap group, n_tile, chunk); chunk fastest so that concurrently running CTAs share
+  // G and X.  i0 / i1: the unit's accumulator range.
+  auto unit_range = [&](int unit, int* cg, int* n_tile, int* pt_begin, int* pt_end, int* i0,
+                        int* i1) {
     *cg = unit % p.chunks_total;
-    const int rest = unit / p.chunks_total;
+    int rest = unit / p.chunks_total;
     *n_tile = rest % p.n_tiles_n;
-    const int ks = rest / p.n_tiles_n;
+    rest /= p.n_tiles_n;
+    const int grp = rest % p.groups;
+    const int ks = rest / p.groups;
+    *i0 = (p.groups == 2 && grp == 1) ? 2 : 0;
+    *i1 = (p.groups == 2 && grp == 0) ? 2 : n_mtiles;
     *pt_begin = static_cast<int>(1LL * pix_tiles * ks / p.ksplit);
     *pt_end = static_cast<int>(1LL * pix_tiles * (ks + 1) / p.ksplit);
   };
@@ -121,8 +137,8 @@ __global__ void __launch_bounds__(kWhThreads, 1)
     // (whole warp converged, one elected lane issues; see conv_gemm.cu)
     uint32_t stage = 0, phase = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      int cg, n_tile, pt0, pt1, s, c;
-      unit_range(unit, &cg, &n_tile, &pt0, &pt1);
+      int cg, n_tile, pt0, pt1, s, c, i0, i1;
+      unit_range(unit, &cg, &n_tile, &pt0, &pt1, &i0, &i1);
       chunk_src(cg, &s, &c);
       const int ox = p.src_off_x[s], oy = p.src_off_y[s];
       int img = pt0 / tiles_per_img;
@@ -134,10 +150,11 @@ __global__ void __launch_bounds__(kWhThreads, 1)
         if (elect_one()) {
           const uint32_t dst = smem_base + stage * stage_bytes;
           const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, a_bytes + kWhBBytes);
+          mbar_expect_tx(fb, a_bytes + static_cast<uint32_t>(n_b_atoms) * kWhBBytes);
           tma_load_4d(dst, &p.a_map[s], fb, c * 64, x0 + ox, y0 + oy, img);
-          tma_load_4d(dst + p.a_stage_bytes, &p.b_map, fb, n_tile * 64, x0 + p.b_off_x,
-                      y0 + p.b_off_y, img);
+          for (int a = 0; a < n_b_atoms; ++a)
+            tma_load_4d(dst + p.a_stage_bytes + a * kWhBBytes, &p.b_map, fb, n_tile * p.BN + a * 64,
+                        x0 + p.b_off_x, y0 + p.b_off_y, img);
         }
         __syncwarp();
         if (++stage == static_cast<uint32_t>(stages)) {
@@ -158,7 +175,8 @@ __global__ void __launch_bounds__(kWhThreads, 1)
     // Descriptors as (lo, hi) words.  lo = start address >> 4 | LBO >> 4 << 16: the LBO of
     // accumulator i is the distance between its two taps' windows (the ones block for the odd
     // tap), the start address advances by two image rows of the halo tile per 16-pixel K step.
-    const uint32_t idesc = make_idesc_bf16(kBlockM, 64, true, true);
+    const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, true, true);
+    const uint32_t bn = static_cast<uint32_t>(p.BN);
     const uint32_t a_hi = desc_hi_sw128(static_cast<uint32_t>(p.Wh) * 128u);
     const uint32_t b_hi = desc_hi_sw128(1024u);
     constexpr int kMaxM = (kMaxTaps + 1) / 2;
@@ -189,8 +207,8 @@ __global__ void __launch_bounds__(kWhThreads, 1)
     const uint32_t d_last = odd ? kstep16 - (kstep16 << 16) : kstep16;
     uint32_t a16 = a16_base;  // start address >> 4 of the current stage
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++unit_it) {
-      int cg, n_tile, pt0, pt1;
-      unit_range(unit, &cg, &n_tile, &pt0, &pt1);
+      int cg, n_tile, pt0, pt1, i0, i1;
+      unit_range(unit, &cg, &n_tile, &pt0, &pt1, &i0, &i1);
       mbar_wait(tempty_bar, (unit_it & 1u) ^ 1u);
       tc_fence_after();
       for (int pt = pt0; pt < pt1; ++pt) {
@@ -200,7 +218,9 @@ __global__ void __launch_bounds__(kWhThreads, 1)
           const uint32_t acc = pt != pt0 ? 1u : 0u;
           const uint32_t b_lo0 = a16 + b_off16 + b_lbo;
           if (p.n_taps == 9) {
-            // 5 accumulators: 4 tap pairs + (tap 8, ones); everything but a16 is loop invariant
+            // 5 accumulators: 4 tap pairs + (tap 8, ones); everything but a16 is loop invariant.
+            // One fully unrolled instruction stream per accumulator range (no predicated-off
+            // tcgen05.mma: they would still occupy the instruction queue).
             uint32_t a_lo[5];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a_lo[i] = a16 + tile_lo[i];
@@ -208,12 +228,30 @@ __global__ void __launch_bounds__(kWhThreads, 1)
               const uint32_t x = a16 + (tile_lo[4] & 0xFFFFu);
               a_lo[4] = x + ((ones16 - x) << 16);
             }
+            if (i0 == 0 && i1 == 5) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {  // 16 pixels (two image rows of the tile) per instruction
+              for (int j = 0; j < 8; ++j) {  // 16 pixels (two image rows of the tile) per instruction
 #pragma unroll
-              for (int i = 0; i < 5; ++i)
-                umma_bf16_lohi(tmem_base + i * 64, a_lo[i] + j * (i == 4 ? d_last : d_pair), a_hi,
-                               b_lo0 + j * 128u, b_hi, idesc, j != 0 ? 1u : acc);
+                for (int i = 0; i < 5; ++i)
+                  umma_bf16_lohi(tmem_base + i * bn, a_lo[i] + j * (i == 4 ? d_last : d_pair), a_hi,
+                                 b_lo0 + j * 128u, b_hi, idesc, j != 0 ? 1u : acc);
+              }
+            } else if (i0 == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                  umma_bf16_lohi(tmem_base + i * bn, a_lo[i] + j * d_pair, a_hi, b_lo0 + j * 128u, b_hi,
+                                 idesc, j != 0 ? 1u : acc);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int i = 2; i < 5; ++i)
+                  umma_bf16_lohi(tmem_base + (i - 2) * bn, a_lo[i] + j * (i == 4 ? d_last : d_pair), a_hi,
+                                 b_lo0 + j * 128u, b_hi, idesc, j != 0 ? 1u : acc);
+              }
             }
           } else {
 #pragma unroll
@@ -224,7 +262,7 @@ __global__ void __launch_bounds__(kWhThreads, 1)
                 if (i < n_mtiles) {
                   uint32_t a_lo = a16 + tile_lo[i] + j * kstep16;
                   if (odd && i == n_mtiles - 1) a_lo += (ones16 - (a_lo & 0x3FFFu)) << 16;
-                  umma_bf16_lohi(tmem_base + i * 64, a_lo, a_hi, b_lo, b_hi, idesc, j != 0 ? 1u : acc);
+                  umma_bf16_lohi(tmem_base + i * bn, a_lo, a_hi, b_lo, b_hi, idesc, j != 0 ? 1u : acc);
                 }
               }
             }
@@ -248,20 +286,20 @@ __global__ void __launch_bounds__(kWhThreads, 1)
     const int m = wq * 32 + lane;
     uint32_t unit_it = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++unit_it) {
-      int cg, n_tile, pt0, pt1;
-      unit_range(unit, &cg, &n_tile, &pt0, &pt1);
+      int cg, n_tile, pt0, pt1, i0, i1;
+      unit_range(unit, &cg, &n_tile, &pt0, &pt1, &i0, &i1);
       mbar_wait(tfull_bar, unit_it & 1u);
       tc_fence_after();
       const bool nonempty = pt1 > pt0;
-      for (int i = 0; i < n_mtiles; ++i) {
+      for (int i = i0; i < i1; ++i) {
         const int tap = 2 * i + (m >> 6);
         const bool is_w = tap < p.n_taps && nonempty;
         const bool is_b = tap == p.n_taps && m == 64 && p.bias_grad != nullptr && cg == 0 && nonempty;
-        float* orow = is_b ? p.bias_grad + n_tile * 64
+        float* orow = is_b ? p.bias_grad + n_tile * p.BN
                            : p.out + (static_cast<long long>(tap * p.chunks_total + cg) * 64 + (m & 63)) * p.ldo +
-                                 n_tile * 64;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + i * 64;
-        for (int ch = 0; ch < 2; ++ch) {
+                                 n_tile * p.BN;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + (i - i0) * p.BN;
+        for (int ch = 0; ch < p.BN / 32; ++ch) {
           uint32_t r[32];
           tmem_ld32(t_row + ch * 32, r);
           tmem_ld_wait();
@@ -330,20 +368,24 @@ int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_do
   p.tiles_x = (d->W + kWhTW - 1) / kWhTW;
   p.tiles_y = (d->H + kWhTH - 1) / kWhTH;
   p.n_img = d->N_img;
-  p.n_tiles_n = d->grad.C / 64;
+  // 128-channel gradient tiles (two tap groups) when the channel count allows it
+  p.BN = (d->grad.C % 128 == 0 && d->n_taps == 9) ? 128 : 64;
+  p.groups = p.BN == 128 ? 2 : 1;
+  p.n_tiles_n = d->grad.C / p.BN;
   p.out = d->out;
   p.ldo = d->ldo;
   p.bias_grad = (d->n_taps % 2 == 1) ? d->bias_grad : nullptr;
 
   const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
-  const int mn_units = p.chunks_total * p.n_tiles_n;
+  const int mn_units = p.chunks_total * p.n_tiles_n * p.groups;
   const int sms = num_sms();
-  // cycles per 128-pixel tile: 8 K steps x ceil(taps / 2) MMAs of 128 x 64 x 16 (48 cycles each,
-  // shared-memory operand bandwidth bound); the single accumulator set is drained by fp32
-  // reductions before the next unit may start
-  p.ksplit = choose_ksplit(mn_units, pix_tiles, sms, 8.0 * ((d->n_taps + 1) / 2) * 48.0, 6000.0, 8);
+  // cycles per 128-pixel tile: 8 K steps x accumulators MMAs of 128 x BN x 16 (48 cycles at BN = 64,
+  // shared-memory operand bandwidth bound; 64 at BN = 128, 2.5 accumulators per unit on average);
+  // the single accumulator set is drained by fp32 reductions before the next unit may start
+  const double tile_cost = p.BN == 128 ? 8.0 * 2.5 * 64.0 : 8.0 * ((d->n_taps + 1) / 2) * 48.0;
+  p.ksplit = choose_ksplit(mn_units, pix_tiles, sms, tile_cost, p.BN == 128 ? 9000.0 : 6000.0, 8);
 
-  const int stage_bytes = static_cast<int>(p.a_stage_bytes) + kWhBBytes;
+  const int stage_bytes = static_cast<int>(p.a_stage_bytes) + (p.BN / 64) * kWhBBytes;
   int stages = (227 * 1024 - 1024 - kOnesBytes - 512) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return -1;

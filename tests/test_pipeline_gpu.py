@@ -138,3 +138,40 @@ def test_train_epoch_semantics(tmp_path):
         ops_i = [op for op in range(8) if np.array_equal(IO.d4(x[i].cpu().numpy(), op), xa[i].cpu().numpy())]
         assert len(ops_i) == 1
         assert np.array_equal(IO.d4(y[i].cpu().numpy(), ops_i[0]), ya[i].cpu().numpy())
+
+
+def test_prefetch_is_transparent(tmp_path):
+    """Staging the next batch with prefetch() (what the epoch loop and bench.py's end-to-end leg do)
+    must not change the training trajectory: two models, same seed, same batches, one fed through
+    prefetch + train_batch, one through train_batch alone.  (Equality up to the summation order of
+    the split-K fp32 atomics, which differs from run to run.)"""
+    rs = np.random.RandomState(5)
+    a, opts = make_model(tmp_path)
+    b, _ = make_model(tmp_path)
+    S, P, B = a.input_size, opts.patch_size, opts.batch_size
+    batches = []
+    for _ in range(4):
+        x = rs.rand(B, S, S, 3).astype(np.float32)
+        y = (rs.rand(B, P, P) < 0.3).astype(np.float64)
+        batches.append((x, y))
+    pinned = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(y.astype(np.uint8)).pin_memory())
+              for x, y in batches]
+    la, lb = [], []
+    a.prefetch(*pinned[0])
+    for i in range(4):
+        if i + 1 < 4:
+            assert a.prefetch(*pinned[i + 1])
+        la.append(a.train_batch(*pinned[i])[0])
+    for x, y in batches:  # plain NumPy batches, no prefetch
+        lb.append(b.train_batch(x, y)[0])
+    assert np.allclose(la, lb, rtol=1e-4, atol=0)
+    pa, pb = a.net.state_dict(), b.net.state_dict()
+    for k in pa:
+        den = max(np.linalg.norm(pb[k]), 1e-12)
+        assert np.linalg.norm(pa[k] - pb[k]) / den < 1e-3, k
+    # a third prefetch while two batches are staged is refused, and training still works
+    a.prefetch(*pinned[0])
+    a.prefetch(*pinned[1])
+    assert a.prefetch(*pinned[2]) is False
+    a.train_batch(*pinned[2])  # not staged: drops the stale entries and stages synchronously
+    assert a.train_batch(*pinned[0])[0] > 0

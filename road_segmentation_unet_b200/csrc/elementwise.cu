@@ -425,7 +425,7 @@ __global__ void maxpool2x2_kernel(const uint4* __restrict__ in, int N, int H, in
 // horizontally adjacent pixels of a window are contiguous in NHWC, so a warp moves 1 KiB runs.
 // WINDOWED = false (no pool below, odd extents allowed): one thread per pixel x 8 channels.
 template <bool WINDOWED>
-__global__ void skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int W, int G,
+__global__ void __launch_bounds__(128, 8) skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int W, int G,
                                  const uint4* __restrict__ dP, const __nv_bfloat16* __restrict__ dC,
                                  long long c_sn, long long c_sy, long long c_sx, int Hc, int Wc,
                                  int crop_y, int crop_x, uint4* __restrict__ dZ) {
@@ -460,46 +460,53 @@ __global__ void skip_grad_kernel(const uint4* __restrict__ Y, int N, int H, int 
                                    : Y + idx[q];
       craw[q] = __ldg(cp);
     }
-    float yv[S * S][8], gr[S * S][8];
-#pragma unroll
-    for (int q = 0; q < S * S; ++q) {
-      unpack8(yraw[q], yv[q]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) gr[q][e] = 0.f;
-    }
+    // arg-max position of every channel's 2x2 window (first maximum wins, like MaxPoolGrad),
+    // two bits per channel; then one output vector at a time, so that only the raw 16-byte
+    // vectors stay live (register pressure decides the occupancy of this HBM-bound kernel)
+    uint32_t argbits = 0;
     if (WINDOWED && dP != nullptr) {
-      float dp[8];
-      unpack8(praw, dp);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        int arg = 0;
-        float best = yv[0][e];
+      for (int w = 0; w < 4; ++w) {
 #pragma unroll
-        for (int q = 1; q < S * S; ++q)
-          if (yv[q][e] > best) {
-            best = yv[q][e];
-            arg = q;
+        for (int h = 0; h < 2; ++h) {
+          int arg = 0;
+          float best = 0.f;
+#pragma unroll
+          for (int q = 0; q < S * S; ++q) {
+            const uint32_t word = w == 0 ? yraw[q].x : w == 1 ? yraw[q].y : w == 2 ? yraw[q].z : yraw[q].w;
+            const float v = h == 0 ? bf16_lo(word) : bf16_hi(word);
+            if (q == 0 || v > best) {
+              best = v;
+              arg = q;
+            }
           }
-#pragma unroll
-        for (int q = 0; q < S * S; ++q)
-          if (arg == q) gr[q][e] = dp[e];
+          argbits |= static_cast<uint32_t>(arg) << (2 * (2 * w + h));
+        }
       }
     }
 #pragma unroll
     for (int q = 0; q < S * S; ++q) {
-      if (in_crop[q]) {
-        float dc[8];
-        unpack8(craw[q], dc);
+      uint32_t ow[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gr[q][e] += dc[e];
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t yw = w == 0 ? yraw[q].x : w == 1 ? yraw[q].y : w == 2 ? yraw[q].z : yraw[q].w;
+        const uint32_t pw = w == 0 ? praw.x : w == 1 ? praw.y : w == 2 ? praw.z : praw.w;
+        const uint32_t cw = w == 0 ? craw[q].x : w == 1 ? craw[q].y : w == 2 ? craw[q].z : craw[q].w;
+        float g2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float yv = h == 0 ? bf16_lo(yw) : bf16_hi(yw);
+          float g = 0.f;
+          if (WINDOWED && dP != nullptr) {
+            const int arg = static_cast<int>((argbits >> (2 * (2 * w + h))) & 3u);
+            if (arg == q) g = h == 0 ? bf16_lo(pw) : bf16_hi(pw);
+          }
+          if (in_crop[q]) g += h == 0 ? bf16_lo(cw) : bf16_hi(cw);
+          g2[h] = yv > 0.f ? g : 0.f;
+        }
+        ow[w] = pack_bf16x2(g2[0], g2[1]);
       }
-    }
-#pragma unroll
-    for (int q = 0; q < S * S; ++q) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (!(yv[q][e] > 0.f)) gr[q][e] = 0.f;
-      dZ[idx[q]] = pack8(gr[q]);
+      dZ[idx[q]] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
 }
@@ -904,8 +911,8 @@ int rsu_skip_grad(const void* Y, int N, int H, int W, int C, const void* dP, con
     const dim3 grid(((W / 2) * (C / 8) + 127) / 128, H / 2, N);
     skip_grad_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
   } else {
-    const dim3 grid((W * (C / 8) + 255) / 256, H, N);
-    skip_grad_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
+    const dim3 grid((W * (C / 8) + 127) / 128, H, N);
+    skip_grad_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(RSU_SKIP_ARGS);
   }
 #undef RSU_SKIP_ARGS
   return check_launch("skip_grad");

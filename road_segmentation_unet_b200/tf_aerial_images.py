@@ -195,6 +195,7 @@ class ConvolutionalModel:
         self._slot_free = [None, None]  # event: the last step that read the slot has consumed it
         self._copy_stream = torch.cuda.Stream()
         self._h_probs = torch.empty(B, P, P, dtype=torch.float32).pin_memory()
+        self._h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         self._reducer = GradientAllReducer(self._dist.dist, self._dist.world, self._net.grads) \
             if self._dist.active else None
         if self._reducer is not None:
@@ -281,6 +282,16 @@ class ConvolutionalModel:
         lr = net.learning_rate(opts.lr)
         net.grads.zero_()
         net.forward(x, y, keep=opts.dropout)
+        # loss and probabilities are final once the forward pass is: their device->host copies run
+        # on the copy stream underneath the backward pass
+        fwd_done = torch.cuda.Event()
+        fwd_done.record(cur)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(fwd_done)
+            self._h_probs.copy_(net.probs, non_blocking=True)
+            self._h_loss.copy_(net.loss, non_blocking=True)
+            fetched = torch.cuda.Event()
+            fetched.record(self._copy_stream)
         net.backward()
         # (the inputs are read by the forward pass and by the first-layer weight gradient at the
         # very end of the backward pass: only now may a prefetch overwrite this slot)
@@ -289,8 +300,10 @@ class ConvolutionalModel:
         self._slot_free[self._slot] = free
         scale = self._reducer.finish() if self._reducer is not None else 1.0
         net.apply_gradients(opts.lr, opts.momentum, scale)
-        self._h_probs.copy_(net.probs, non_blocking=True)
-        loss = float(net.loss.item())  # synchronises: loss and probabilities are fetched every step
+        # the step's fetches (loss, probabilities) are what the caller waits for; the update that
+        # follows them on the stream is ordered before everything the next call enqueues
+        fetched.synchronize()
+        loss = float(self._h_loss[0])
         if self._dist.active:
             t = torch.tensor([loss], device="cuda")
             self._dist.dist.all_reduce(t)

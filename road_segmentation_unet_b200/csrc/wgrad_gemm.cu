@@ -10,6 +10,9 @@
 // `ksplit` CTAs whose partial sums are combined with fp32 atomics into the zero-initialised
 // output, which has TensorFlow's HWIO kernel layout [(tap, cin), cout].
 // Out-of-range pixels of either operand arrive as zeros from TMA and contribute nothing.
+// BiasAddGrad (the column sums of G) rides along: one more 64-row atom whose operand is a constant
+// block of ones in shared memory -- the free second atom of the last row tile when the atom count
+// is odd, else one extra row tile -- so no separate pass over G is needed.
 //
 // Reference op replaced: Conv2DBackpropFilter of every tf.layers.conv2d / conv2d_transpose in
 // src/unet.py:34-45, 67, 88-91.
@@ -22,6 +25,7 @@
 namespace rsu {
 
 constexpr int kWgThreads = 256;
+constexpr int kWgOnesBytes = 4096;  // two 16-row K slices of bf16 ones
 constexpr int kWgTmemCols = 512;
 constexpr int kWgAccStride = 256;
 
@@ -46,7 +50,8 @@ __device__ __forceinline__ AtomCoord decode_atom(const WgradParams& p, int atom,
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-    wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int stages, uint32_t atom_bytes) {
+    wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int stages, uint32_t atom_bytes,
+                      float* bias_grad) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -54,7 +59,10 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 
   const int n_b_atoms = p.BN / 64;
   const uint32_t stage_bytes = static_cast<uint32_t>(2 + n_b_atoms) * atom_bytes;
-  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  const uint32_t ones_base = smem_base + stages * stage_bytes;
+  const uint32_t bar_base = ones_base + kWgOnesBytes;
+  // (with a bias gradient the atom list is one longer: atom n_atoms = the ones block)
+  const int n_atoms_all = p.n_atoms + (bias_grad != nullptr ? 1 : 0);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
@@ -67,6 +75,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&p.a_map[s]);
     tma_prefetch_desc(&p.b_map);
+  }
+  {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (ones_base - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kWgThreads) ones[i] = 0x3F803F80u;
+    fence_proxy_async();
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -116,9 +129,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       int m_tile, n_tile, pt0, pt1;
       unit_range(unit, &m_tile, &n_tile, &pt0, &pt1);
       const int atom0 = m_tile * 2;
-      const int n_a = (atom0 + 1 < p.n_atoms) ? 2 : 1;
-      const AtomCoord a0 = decode_atom(p, atom0, chunks_total);
-      const AtomCoord a1 = decode_atom(p, n_a == 2 ? atom0 + 1 : atom0, chunks_total);
+      // real (TMA-loaded) atoms of this row tile: 2, 1 (odd tail, or + the ones atom) or 0 (the
+      // ones atom alone)
+      const int n_a = atom0 + 1 < p.n_atoms ? 2 : (atom0 < p.n_atoms ? 1 : 0);
+      const AtomCoord a0 = decode_atom(p, n_a >= 1 ? atom0 : 0, chunks_total);
+      const AtomCoord a1 = decode_atom(p, n_a == 2 ? atom0 + 1 : 0, chunks_total);
       const int n0 = n_tile * p.BN;
       const uint32_t tx_bytes = static_cast<uint32_t>(is_a ? n_a : n_b_atoms) * box_bytes;
       const int bx = p.b_off_x, by = p.b_off_y;
@@ -133,7 +148,8 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           const uint32_t fb = full_bar(stage);
           mbar_expect_tx(fb, tx_bytes);
           if (is_a) {
-            tma_load_4d(dst, &p.a_map[a0.src], fb, a0.chunk * 64, x0 + a0.dx, y0 + a0.dy, img);
+            if (n_a >= 1)
+              tma_load_4d(dst, &p.a_map[a0.src], fb, a0.chunk * 64, x0 + a0.dx, y0 + a0.dy, img);
             if (n_a == 2)
               tma_load_4d(dst + atom_bytes, &p.a_map[a1.src], fb, a1.chunk * 64, x0 + a1.dx, y0 + a1.dy,
                           img);
@@ -160,6 +176,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, true, true);
     const uint32_t hi = desc_hi_sw128(1024u);
+    const uint32_t ones16 = (ones_base >> 4) & 0x3FFFu;
     uint32_t stage = 0, phase = 0;
     uint32_t acc_it = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++acc_it) {
@@ -170,12 +187,30 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kWgAccStride;
+      // 0: no ones atom in this row tile, 1: second atom = ones, 2: first atom = ones
+      const int ones_kind = bias_grad == nullptr ? 0
+                            : (m_tile * 2 + 1 == p.n_atoms ? 1 : (m_tile * 2 == p.n_atoms ? 2 : 0));
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint32_t a_lo = desc_lo_sw128(a_addr, atom_bytes);
+          // A descriptor (lo word) of K slice 0 and its advance per 16-pixel slice:
+          //   two real atoms / one real atom: start = stage, LBO = atom stride, + 2 KiB per slice
+          //   real atom + ones atom: LBO = distance to the ones block (shrinks as the start advances)
+          //   ones atom alone: start = ones block, never advances
+          uint32_t a_lo, a_step;
+          if (ones_kind == 0) {
+            a_lo = desc_lo_sw128(a_addr, atom_bytes);
+            a_step = 128u;
+          } else if (ones_kind == 1) {
+            const uint32_t s16 = (a_addr >> 4) & 0x3FFFu;
+            a_lo = s16 | ((ones16 - s16) << 16);
+            a_step = 128u - (128u << 16);
+          } else {
+            a_lo = ones16 | (128u << 16);
+            a_step = 0u;
+          }
           const uint32_t b_lo = desc_lo_sw128(a_addr + 2 * atom_bytes, atom_bytes);
           const uint32_t first = pt != pt0 ? 1u : 0u;
           // 16 pixels (K) per instruction = 16 rows of 128 B = 2 KiB further into every atom.
@@ -184,12 +219,12 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           if (mma_per_tile == 4) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              umma_bf16_lohi(d_tmem, a_lo + j * 128u, hi, b_lo + j * 128u, hi, idesc, j != 0 ? 1u : first);
+              umma_bf16_lohi(d_tmem, a_lo + j * a_step, hi, b_lo + j * 128u, hi, idesc, j != 0 ? 1u : first);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (j < mma_per_tile)
-                umma_bf16_lohi(d_tmem, a_lo + j * 128u, hi, b_lo + j * 128u, hi, idesc, j != 0 ? 1u : first);
+                umma_bf16_lohi(d_tmem, a_lo + j * a_step, hi, b_lo + j * 128u, hi, idesc, j != 0 ? 1u : first);
             }
           }
           umma_commit(empty_bar(stage));
@@ -214,8 +249,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       const uint32_t acc = acc_it & 1u;
       const uint32_t acc_phase = (acc_it >> 1) & 1u;
       const int atom = m_tile * 2 + (m >> 6);
-      const bool valid = atom < p.n_atoms && pt1 > pt0;
-      float* orow = p.out + (static_cast<long long>(atom) * 64 + (m & 63)) * p.ldo + n_tile * p.BN;
+      // the ones atom: its 64 rows all hold the column sums of G; row 0 goes to the bias gradient
+      const bool is_bias = bias_grad != nullptr && atom == p.n_atoms && (m & 63) == 0;
+      const bool valid = (atom < p.n_atoms || is_bias) && pt1 > pt0;
+      float* orow = is_bias ? bias_grad + n_tile * p.BN
+                            : p.out + (static_cast<long long>(atom) * 64 + (m & 63)) * p.ldo + n_tile * p.BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row =
@@ -336,7 +374,9 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
     p.tap_dx[t] = d->tap_dx[t];
   }
   p.n_atoms = d->n_taps * chunks_total;
-  p.n_tiles_m = (p.n_atoms + 1) / 2;
+  float* bias_grad = d->bias_grad;  // column sums of G through one more (ones) atom
+  if (bias_grad && (reinterpret_cast<uintptr_t>(bias_grad) & 15)) bias_grad = nullptr;
+  p.n_tiles_m = (p.n_atoms + (bias_grad ? 1 : 0) + 1) / 2;
   const int cout = d->grad.C;
   p.BN = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
   p.n_tiles_n = cout / p.BN;
@@ -352,10 +392,10 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
 
   const int atom_bytes = ((TW * TH * 128) + 1023) & ~1023;
   const int stage_bytes = (2 + p.BN / 64) * atom_bytes;
-  int stages = (220 * 1024) / stage_bytes;
+  int stages = (220 * 1024 - kWgOnesBytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
-  const int smem = 1024 + stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+  const int smem = 1024 + stages * stage_bytes + kWgOnesBytes + 8 * (2 * stages + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     RSU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel,
@@ -365,6 +405,8 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   const long long total = 1LL * mn_units * p.ksplit;
   int grid = num_sms();
   if (total < grid) grid = static_cast<int>(total);
-  wgrad_gemm_kernel<<<grid, kWgThreads, smem, stream>>>(p, stages, static_cast<uint32_t>(atom_bytes));
+  wgrad_gemm_kernel<<<grid, kWgThreads, smem, stream>>>(p, stages, static_cast<uint32_t>(atom_bytes),
+                                                        bias_grad);
+  if (bias_grad && d->bias_done_host) *d->bias_done_host = 1;
   return check_launch("wgrad_gemm_kernel");
 }

@@ -132,6 +132,15 @@ def test_conv3x3_wgrad(ops, case):
     out = torch.zeros(9 * cin, cout, dtype=torch.float32, device="cuda")
     ops.conv3x3_wgrad([(dev(x), 0, 0)], dev(dz), out, dilation=d)
     assert rel_err(out.cpu().numpy(), ref) < 2e-3
+    # the same with BiasAddGrad riding along (ones atom: free second atom when 9*cin/64 is odd,
+    # an extra row tile when it is even); accumulated into
+    out2 = torch.zeros(9 * cin, cout, dtype=torch.float32, device="cuda")
+    db = torch.full((cout,), 0.25, dtype=torch.float32, device="cuda")
+    done = ops.conv3x3_wgrad([(dev(x), 0, 0)], dev(dz), out2, dilation=d, bias_grad=db,
+                             algo=ops.ALGO_PER_TAP)
+    assert done
+    assert rel_err(out2.cpu().numpy(), ref) < 2e-3
+    assert rel_err(db.cpu().numpy() - 0.25, dz.astype(np.float64).sum(axis=(0, 1, 2))) < 2e-3
 
 
 def test_conv3x3_wgrad_concat(ops):

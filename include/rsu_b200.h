@@ -72,6 +72,10 @@ typedef struct {
   long long mask_sn, mask_sy, mask_sx;
   int accumulate; /* out += result */
   int algo;       /* 0 = choose, 1 = one TMA box per tap, 2 = halo tile shared by all taps */
+  /* mask_nc > 0: the mask tensor has mask_nc channels and covers output channels
+   * [mask_c0, mask_c0 + mask_nc) only (the ReluGrad of one member of a concat gradient,
+   * unet.py:70-85); both multiples of the N tile (64 / 128 / 256, the largest dividing Ntot). */
+  int mask_c0, mask_nc;
 } rsu_conv_gemm_desc;
 int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream);
 

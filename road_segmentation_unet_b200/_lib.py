@@ -28,7 +28,8 @@ class ConvGemmDesc(C.Structure):
                 ("out_sn", C.c_longlong), ("out_sy", C.c_longlong), ("out_sx", C.c_longlong),
                 ("shuffle_cout", C.c_int), ("bias", C.c_void_p), ("relu", C.c_int),
                 ("mask", C.c_void_p), ("mask_sn", C.c_longlong), ("mask_sy", C.c_longlong),
-                ("mask_sx", C.c_longlong), ("accumulate", C.c_int), ("algo", C.c_int)]
+                ("mask_sx", C.c_longlong), ("accumulate", C.c_int), ("algo", C.c_int),
+                ("mask_c0", C.c_int), ("mask_nc", C.c_int)]
 
 
 class WgradDesc(C.Structure):

@@ -182,8 +182,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       }
       // ReLU-gradient mask bits of this tile, fetched while the MMAs are still running
       uint32_t mbits[2][4];
-      if (p.mask != nullptr) {
-        const __nv_bfloat16* mpx = p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + n0;
+      // (a partial mask covers whole N tiles: mask_c0 / mask_nc are multiples of BN)
+      const bool tile_masked =
+          p.mask != nullptr && (p.mask_nc == 0 || (n0 >= p.mask_c0 && n0 < p.mask_c0 + p.mask_nc));
+      if (tile_masked) {
+        const __nv_bfloat16* mpx =
+            p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + (n0 - p.mask_c0);
         load_mask_bits4(mpx, p.BN / 32, valid, mbits[0]);
         load_mask_bits4(mpx + 128, p.BN / 32 - 4, valid, mbits[1]);
       }
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (p.mask != nullptr) {
+          if (tile_masked) {
             uint32_t mb = 0;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
@@ -361,6 +365,12 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
   p.mask_sn = d->mask_sn;
   p.mask_sy = d->mask_sy;
   p.mask_sx = d->mask_sx;
+  p.mask_c0 = d->mask_nc > 0 ? d->mask_c0 : 0;
+  p.mask_nc = d->mask_nc;
+  if (d->mask && d->mask_nc > 0 && (d->mask_c0 % p.BN || d->mask_nc % p.BN || d->mask_c0 < 0 ||
+                                    d->mask_c0 + d->mask_nc > d->Ntot))
+    return set_error(RSU_EINVAL, "mask channel range [%d, +%d) not a multiple of the N tile %d", d->mask_c0,
+                     d->mask_nc, p.BN);
   p.accumulate = d->accumulate;
 
   int stages;

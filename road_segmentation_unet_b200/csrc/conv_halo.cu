@@ -55,6 +55,7 @@ struct ConvHaloParams {
   int relu;
   const __nv_bfloat16* mask;
   long long mask_sn, mask_sy, mask_sx;
+  int mask_c0, mask_nc;  // mask_nc > 0: the mask covers output channels [mask_c0, +mask_nc) only
   int accumulate;
   // Coalesced epilogue (used unless accumulate): 64-channel x 128-pixel blocks are staged in
   // shared memory (128-byte swizzle) and written with TMA stores; the ReLU-gradient mask blocks
@@ -362,12 +363,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       *bimg = img;
       return true;
     };
+    // (with a partial mask every block still fetches a mask tile -- blocks outside the masked
+    // channel range fetch channel 0 and ignore it -- so that the two-deep tile pipeline and its
+    // barrier phases do not depend on the block)
+    auto mask_chan = [&](int c0) -> int {
+      if (p.mask_nc == 0) return c0;
+      const int c = c0 - p.mask_c0;
+      return (c >= 0 && c < p.mask_nc) ? c : 0;
+    };
     auto issue_mask = [&](long long q) {
       int c0, bx, by, bimg;
       if (block_coords(q, &c0, &bx, &by, &bimg)) {
         const uint32_t bar = mfull_base + 8u * static_cast<uint32_t>(q & 1);
         mbar_expect_tx(bar, 16384u);
-        tma_load_4d(mask_stg + static_cast<uint32_t>(q & 1) * 16384u, &p.mask_map, bar, c0, bx, by, bimg);
+        tma_load_4d(mask_stg + static_cast<uint32_t>(q & 1) * 16384u, &p.mask_map, bar, mask_chan(c0), bx,
+                    by, bimg);
       }
     };
     if (has_mask && leader) {
@@ -416,7 +426,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (has_mask) {
+            if (has_mask && (p.mask_nc == 0 || (n0 + cb * 64 >= p.mask_c0 &&
+                                                n0 + cb * 64 < p.mask_c0 + p.mask_nc))) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const uint4 mv = ld_shared_v4(mask_stg + buf * 16384u + row_off +
@@ -477,13 +488,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       }
       // ReLU-gradient mask bits of this unit, fetched while the MMAs are still running
       uint32_t mbits[2][4];
-      if (p.mask != nullptr) {
+      const bool tile_masked =
+          p.mask != nullptr && (p.mask_nc == 0 || (n0 >= p.mask_c0 && n0 < p.mask_c0 + p.mask_nc));
+      if (tile_masked) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const int y = (ty * p.MT + mt) * kHaloTH + ly;
           const bool valid = mt < p.MT && y < p.H_out && x < p.W_out;
-          load_mask_bits4(p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + n0, p.BN / 32,
-                          valid, mbits[mt]);
+          load_mask_bits4(p.mask + img * p.mask_sn + y * p.mask_sy + x * p.mask_sx + (n0 - p.mask_c0),
+                          p.BN / 32, valid, mbits[mt]);
         }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -513,7 +526,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (p.mask != nullptr) {
+            if (tile_masked) {
               const uint32_t mb = mt == 0 ? (ch == 0 ? mbits[0][0] : ch == 1 ? mbits[0][1] : ch == 2 ? mbits[0][2] : mbits[0][3])
                                           : (ch == 0 ? mbits[1][0] : ch == 1 ? mbits[1][1] : ch == 2 ? mbits[1][2] : mbits[1][3]);
 #pragma unroll
@@ -662,6 +675,12 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
   p.mask_sn = d->mask_sn;
   p.mask_sy = d->mask_sy;
   p.mask_sx = d->mask_sx;
+  p.mask_c0 = d->mask_nc > 0 ? d->mask_c0 : 0;
+  p.mask_nc = d->mask_nc;
+  if (d->mask && d->mask_nc > 0 && (d->mask_c0 % p.BN || d->mask_nc % p.BN || d->mask_c0 < 0 ||
+                                    d->mask_c0 + d->mask_nc > d->Ntot))
+    return set_error(RSU_EINVAL, "mask channel range [%d, +%d) not a multiple of the N tile %d", d->mask_c0,
+                     d->mask_nc, p.BN);
   p.accumulate = d->accumulate;
   p.tma_epilogue = tma_epi ? 1 : 0;
   if (tma_epi) {
@@ -679,6 +698,7 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
     if (rc) return rc;
     if (d->mask) {
       ov.ptr = d->mask;
+      if (d->mask_nc > 0) ov.C = d->mask_nc;
       ov.sn = d->mask_sn;
       ov.sy = d->mask_sy;
       ov.sx = d->mask_sx;

@@ -37,6 +37,7 @@ struct ConvGemmParams {
   // optional ReLU-gradient mask: keep value only where mask[...] > 0 (same indexing as out)
   const __nv_bfloat16* mask;
   long long mask_sn, mask_sy, mask_sx;
+  int mask_c0, mask_nc;  // mask_nc > 0: mask covers output channels [mask_c0, mask_c0 + mask_nc) only
   int accumulate;  // out += result (read-modify-write)
 };
 

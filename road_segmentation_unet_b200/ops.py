@@ -73,7 +73,7 @@ ALGO_AUTO, ALGO_PER_TAP, ALGO_HALO = 0, 1, 2
 
 
 def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None, accumulate=False,
-              shuffle_cout=0, grid_hw=None, algo=ALGO_AUTO):
+              shuffle_cout=0, grid_hw=None, algo=ALGO_AUTO, mask_c0=0):
     """Generic implicit GEMM (rsu_conv_gemm).  srcs: list of (tensor_or_View, off_y, off_x).
     algo: 0 = library's choice, 1 = one TMA box per tap, 2 = halo tile shared by all taps."""
     d = ConvGemmDesc()
@@ -95,9 +95,12 @@ def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None,
     d.bias = _ptr(bias)
     d.relu = int(relu)
     if mask is not None:
-        assert mask.shape == out.shape
+        # a mask with fewer channels than `out` covers output channels [mask_c0, mask_c0 + C_mask)
+        assert mask.shape[:3] == out.shape[:3] and mask.shape[3] <= out.shape[3]
         d.mask = _ptr(mask)
         d.mask_sn, d.mask_sy, d.mask_sx = mask.stride()[:3]
+        if mask.shape[3] != out.shape[3]:
+            d.mask_c0, d.mask_nc = int(mask_c0), int(mask.shape[3])
     d.accumulate = int(accumulate)
     d.algo = int(algo)
     _timed("conv_gemm", call, "rsu_conv_gemm", C.byref(d))
@@ -173,11 +176,12 @@ def conv3x3_fwd(srcs, w_fwd, bias, out, dilation=1, relu=True, algo=ALGO_AUTO):
     conv_gemm(srcs, conv_taps(dilation), w_fwd, out, out.shape[3], bias=bias, relu=relu, algo=algo)
 
 
-def conv3x3_dgrad(dz, w_dgrad, dx_window, dilation=1, mask=None, accumulate=False, algo=ALGO_AUTO):
+def conv3x3_dgrad(dz, w_dgrad, dx_window, dilation=1, mask=None, accumulate=False, algo=ALGO_AUTO,
+                  mask_c0=0):
     """dx_window[u,v] = sum_taps dz[u - ky*d, v - kx*d] W[ky,kx]^T over the touched input window
     (extent = dz extent + 2*dilation); optional fused ReLU mask / accumulation."""
     conv_gemm([(dz, 0, 0)], conv_taps(dilation, -1), w_dgrad, dx_window, dx_window.shape[3],
-              mask=mask, accumulate=accumulate, algo=algo)
+              mask=mask, accumulate=accumulate, algo=algo, mask_c0=mask_c0)
 
 
 def conv3x3_wgrad(srcs, dz, dw, dilation=1, bias_grad=None, algo=ALGO_AUTO):

@@ -254,7 +254,7 @@ class UNet:
                 self.D2.append(self._bf(B, t, t, f[i]))
                 if tr:
                     self.dD1.append(self._bf(B, t + 4, t + 4, f[i]))
-                    self.dD2.append(self._bf(B, t, t, f[i]))
+                    self.dD2.append(None)  # a channel slice of the concat gradient, set below
             else:
                 self.dil_off.append(None)
                 self.D1.append(None)
@@ -290,6 +290,10 @@ class UNet:
                 self.dCat.append(self._bf(B, t, t, fo * (3 if self.dilated else 2)))
                 self.dC1.append(self._bf(B, t - 2, t - 2, fo))
                 self.dC2.append(self._bf(B, t - 4, t - 4, fo))
+                if self.dilated:
+                    # d(dilated skip): the data-gradient kernel of conv_{L+j}/conv1 applies the
+                    # ReLU mask of D2 to this channel range while it writes the concat gradient
+                    self.dD2[L - 2 - j] = self.dCat[j][..., fo:2 * fo]
         P = self.P
         dev = self.device
         self.probs = torch.empty(B, P, P, dtype=torch.float32, device=dev)
@@ -470,7 +474,7 @@ class UNet:
     def _tag(self, name):
         ops.set_layer(name, self._flops.get(name, 0.0))
 
-    def _conv_bwd(self, conv, srcs, dz, dx, mask=None, accumulate=False, need_dx=True):
+    def _conv_bwd(self, conv, srcs, dz, dx, mask=None, accumulate=False, need_dx=True, mask_c0=0):
         """wgrad + bias grad (+ dgrad) of one 3x3 convolution."""
         self._tag(conv.name)
         g = lambda n: self.var(conv.name + "/" + n, "grads")
@@ -479,7 +483,7 @@ class UNet:
             ops.bias_grad(dz, g("bias"))
         if need_dx:
             ops.conv3x3_dgrad(dz, conv.w_dgrad, dx, dilation=conv.dilation, mask=mask,
-                              accumulate=accumulate)
+                              accumulate=accumulate, mask_c0=mask_c0)
 
     def _first_bwd(self, conv, col, which_dcol, dz, dilation, oy, ox):
         """Cin = 3 convolution through its im2col matrix, plus d(color_space_adjust)."""
@@ -533,10 +537,11 @@ class UNet:
             if self.dilated:
                 srcs.append((self.D2[i], 0, 0))
             srcs.append((self.U[j], 0, 0))
-            self._conv_bwd(c1, srcs, self.dC1[j], self.dCat[j])
+            # (dilated nets: ReluGrad of the dilated skip D2 is applied to channels [fo, 2 fo) of
+            # the concat gradient by this kernel's epilogue; dD2 is that slice)
+            self._conv_bwd(c1, srcs, self.dC1[j], self.dCat[j],
+                           mask=self.D2[i] if self.dilated else None, mask_c0=fo)
             dcat = self.dCat[j]
-            if self.dilated:
-                ops.relu_mask(self.D2[i], dcat[..., fo:2 * fo], self.dD2[i])
             d_up = dcat[..., (2 if self.dilated else 1) * fo:]
             x_in = self._dec_in[j]
             g = lambda n: self.var(up.name + "/" + n, "grads")

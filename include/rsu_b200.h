@@ -76,6 +76,13 @@ typedef struct {
    * [mask_c0, mask_c0 + mask_nc) only (the ReluGrad of one member of a concat gradient,
    * unet.py:70-85); both multiples of the N tile (64 / 128 / 256, the largest dividing Ntot). */
   int mask_c0, mask_nc;
+  /* optional fused 2x2 / stride-2 max pool of the (ReLU) output (tf.layers.max_pooling2d,
+   * unet.py:52): bf16 [N_img, H_out/2, W_out/2, Ntot] with element strides.  Only the halo-tile
+   * kernel's coalesced epilogue implements it; *pool_done_host tells whether it was written
+   * (0: the caller still has to run rsu_maxpool2x2). */
+  void* pool_out;
+  long long pool_sn, pool_sy, pool_sx;
+  int* pool_done_host;
 } rsu_conv_gemm_desc;
 int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream);
 

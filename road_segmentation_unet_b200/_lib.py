@@ -29,7 +29,9 @@ class ConvGemmDesc(C.Structure):
                 ("shuffle_cout", C.c_int), ("bias", C.c_void_p), ("relu", C.c_int),
                 ("mask", C.c_void_p), ("mask_sn", C.c_longlong), ("mask_sy", C.c_longlong),
                 ("mask_sx", C.c_longlong), ("accumulate", C.c_int), ("algo", C.c_int),
-                ("mask_c0", C.c_int), ("mask_nc", C.c_int)]
+                ("mask_c0", C.c_int), ("mask_nc", C.c_int), ("pool_out", C.c_void_p),
+                ("pool_sn", C.c_longlong), ("pool_sy", C.c_longlong), ("pool_sx", C.c_longlong),
+                ("pool_done_host", C.POINTER(C.c_int))]
 
 
 class WgradDesc(C.Structure):

@@ -300,6 +300,7 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
     return set_error(RSU_EINVAL, "shuffle_cout %d inconsistent with Ntot %d", d->shuffle_cout,
                      d->Ntot);
 
+  if (d->pool_done_host) *d->pool_done_host = 0;
   // Halo-tile kernel for the layers whose per-tap operand traffic (L2 -> SM) bounds them: few
   // output channels per tile and a large pixel grid.
   // (thresholds from the per-layer A/B table, profiles/r1_layers_ab.md)

@@ -63,6 +63,9 @@ struct ConvHaloParams {
   int tma_epilogue;
   CUtensorMap out_map;   // 4-D (C, W, H, N) bf16, box {64, 8, 16, 1}
   CUtensorMap mask_map;  // same geometry over the mask tensor
+  // fused 2x2 max pool of the ReLU output (TMA epilogue only): 64-channel x 32-pixel blocks
+  int pool;
+  CUtensorMap pool_map;  // 4-D (C, W/2, H/2, N) bf16, box {64, 4, 8, 1}
 };
 
 struct HaloIssueCtx {
@@ -194,8 +197,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   const int lane = threadIdx.x & 31;
 
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.BN) * 128u;
-  const uint32_t b_base = smem_base + p.stages_a * p.a_stage_bytes +
-                          (p.tma_epilogue ? (p.mask != nullptr ? 4u : 2u) * 16384u : 0u);
+  const uint32_t stg_bytes_k = (p.tma_epilogue ? (p.mask != nullptr ? 4u : 2u) * 16384u : 0u) +
+                               (p.pool ? 2u * 4096u : 0u);
+  const uint32_t b_base = smem_base + p.stages_a * p.a_stage_bytes + stg_bytes_k;
   const uint32_t bar_base = b_base + p.stages_b * b_stage_bytes;
   // barriers: a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] tfull[2] tempty[2]
   const int SA = p.stages_a, SB = p.stages_b;
@@ -208,7 +212,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
   const uint32_t bias_base = tmem_slot + 16u;  // float [2][128]
   // epilogue staging: out[2] (16 KiB each) then mask[2]; placed before the barriers, 1024-aligned
-  const uint32_t stg_base = b_base - (p.tma_epilogue ? (p.mask != nullptr ? 4u : 2u) * 16384u : 0u);
+  const uint32_t stg_base = b_base - stg_bytes_k;
+  const uint32_t pool_stg = b_base - 2u * 4096u;  // (only meaningful when p.pool)
   const uint32_t mfull_base = bias_base + 2u * 128u * 4u;  // mask_full[2] mbarriers
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     if (p.tma_epilogue) {
       tma_prefetch_desc(&p.out_map);
       if (p.mask != nullptr) tma_prefetch_desc(&p.mask_map);
+      if (p.pool) tma_prefetch_desc(&p.pool_map);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -451,11 +457,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             st_shared_v4(out_stg + buf * 16384u + row_off + ((static_cast<uint32_t>(c) ^ swz) << 4), packed[c]);
+          if (p.pool) {
+            // 2x2 max pool of the block: the window of pixel (ly, lx) = lanes {m, m^1, m^8} of this
+            // warp (8-pixel-wide tile rows); ReLU outputs are >= 0, so the bf16 maximum is the
+            // unsigned maximum of the 16-bit patterns.  Lanes with even (ly, lx) own a pooled pixel.
+            uint4 pooled[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              uint32_t w[4] = {packed[c].x, packed[c].y, packed[c].z, packed[c].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                w[e] = __vmaxu2(w[e], __shfl_xor_sync(0xffffffffu, w[e], 1));
+                w[e] = __vmaxu2(w[e], __shfl_xor_sync(0xffffffffu, w[e], 8));
+              }
+              pooled[c] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if ((m & 1) == 0 && (m & 8) == 0) {
+              const uint32_t pr = static_cast<uint32_t>(((m >> 4) << 2) | ((m & 7) >> 1));  // (ly/2)*4 + lx/2
+              const uint32_t prow = pool_stg + buf * 4096u + pr * 128u;
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                st_shared_v4(prow + ((static_cast<uint32_t>(c) ^ (pr & 7u)) << 4), pooled[c]);
+            }
+          }
           fence_proxy_async();
           named_bar_sync(2, 128);  // barrier B: block complete in smem, mask block fully consumed
           if (leader) {
             tma_store_4d(&p.out_map, out_stg + buf * 16384u, n0 + cb * 64, tx * kHaloTW,
                          (ty * p.MT + mt) * kHaloTH, img);
+            if (p.pool)
+              tma_store_4d(&p.pool_map, pool_stg + buf * 4096u, n0 + cb * 64, tx * (kHaloTW / 2),
+                           (ty * p.MT + mt) * (kHaloTH / 2), img);
             tma_store_commit();
             if (has_mask) issue_mask(q + 2);
             tma_store_wait_read<1>();  // the other staging buffer is free again
@@ -588,7 +620,10 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
   for (int s = 0; s < d->n_src; ++s) chunks_total += d->src[s].C / 64;
   const int num_k = d->n_taps * chunks_total;
   const int smem_max = 227 * 1024 - 1024 /*align*/ - 2048 /*barriers, bias*/;
-  const int stg_full = (d->mask ? 4 : 2) * 16384;  // staging of the TMA epilogue
+  // fused max pool: ReLU epilogue without mask / accumulation, even output extents
+  const bool want_pool = d->pool_out != nullptr && d->relu && !d->mask && !d->accumulate &&
+                         d->H_out % 2 == 0 && d->W_out % 2 == 0;
+  const int stg_full = (d->mask ? 4 : 2) * 16384 + (want_pool ? 2 * 4096 : 0);  // staging of the TMA epilogue
 
   ConvHaloParams p;
   memset(&p, 0, sizeof(p));
@@ -683,6 +718,21 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
                      d->mask_nc, p.BN);
   p.accumulate = d->accumulate;
   p.tma_epilogue = tma_epi ? 1 : 0;
+  p.pool = (want_pool && tma_epi) ? 1 : 0;
+  if (p.pool) {
+    rsu_view pv;
+    pv.ptr = d->pool_out;
+    pv.C = d->Ntot;
+    pv.H = d->H_out / 2;
+    pv.W = d->W_out / 2;
+    pv.N = d->N_img;
+    pv.sn = d->pool_sn;
+    pv.sy = d->pool_sy;
+    pv.sx = d->pool_sx;
+    pv.off_y = pv.off_x = 0;
+    int rc = encode_act_map(&p.pool_map, pv, kHaloTW / 2, kHaloTH / 2);
+    if (rc) return rc;
+  }
   if (tma_epi) {
     rsu_view ov;
     ov.ptr = d->out;
@@ -728,6 +778,7 @@ int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forc
     grid = total < sms ? static_cast<int>(total) : sms;
   }
   conv_halo_kernel<<<grid, kHaloThreads, smem, stream>>>(p);
+  if (p.pool && d->pool_done_host) *d->pool_done_host = 1;
   return check_launch("conv_halo_kernel");
 }
 

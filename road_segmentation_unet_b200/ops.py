@@ -73,7 +73,7 @@ ALGO_AUTO, ALGO_PER_TAP, ALGO_HALO = 0, 1, 2
 
 
 def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None, accumulate=False,
-              shuffle_cout=0, grid_hw=None, algo=ALGO_AUTO, mask_c0=0):
+              shuffle_cout=0, grid_hw=None, algo=ALGO_AUTO, mask_c0=0, pool_out=None):
     """Generic implicit GEMM (rsu_conv_gemm).  srcs: list of (tensor_or_View, off_y, off_x).
     algo: 0 = library's choice, 1 = one TMA box per tap, 2 = halo tile shared by all taps."""
     d = ConvGemmDesc()
@@ -103,7 +103,14 @@ def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None,
             d.mask_c0, d.mask_nc = int(mask_c0), int(mask.shape[3])
     d.accumulate = int(accumulate)
     d.algo = int(algo)
+    pooled = C.c_int(0)
+    if pool_out is not None:
+        assert pool_out.shape == (n, h // 2, w // 2, out.shape[3])
+        d.pool_out = _ptr(pool_out)
+        d.pool_sn, d.pool_sy, d.pool_sx = pool_out.stride()[:3]
+        d.pool_done_host = C.pointer(pooled)
     _timed("conv_gemm", call, "rsu_conv_gemm", C.byref(d))
+    return bool(pooled.value)
 
 
 def wgrad_gemm(srcs, taps, grad, grad_off, out, grid_hw, bias_grad=None, algo=ALGO_AUTO):
@@ -171,9 +178,11 @@ class PackPlan:
 
 
 # ------------------------------------------------------------------ conv 3x3 (unet.py:34-45,88-91)
-def conv3x3_fwd(srcs, w_fwd, bias, out, dilation=1, relu=True, algo=ALGO_AUTO):
-    """srcs: [(tensor, off_y, off_x)] in concat order; out [N,Ho,Wo,Cout] bf16."""
-    conv_gemm(srcs, conv_taps(dilation), w_fwd, out, out.shape[3], bias=bias, relu=relu, algo=algo)
+def conv3x3_fwd(srcs, w_fwd, bias, out, dilation=1, relu=True, algo=ALGO_AUTO, pool_out=None):
+    """srcs: [(tensor, off_y, off_x)] in concat order; out [N,Ho,Wo,Cout] bf16.  pool_out: the 2x2
+    max pool of `out`, written by the same kernel when it can (returns True), else untouched."""
+    return conv_gemm(srcs, conv_taps(dilation), w_fwd, out, out.shape[3], bias=bias, relu=relu, algo=algo,
+                     pool_out=pool_out)
 
 
 def conv3x3_dgrad(dz, w_dgrad, dx_window, dilation=1, mask=None, accumulate=False, algo=ALGO_AUTO,

@@ -413,8 +413,9 @@ class UNet:
                 self._tag(d2.name)
                 ops.conv3x3_fwd([(self.D1[i], 0, 0)], d2.w_fwd, bias(d2.name), self.D2[i], dilation=2)
             self._tag(reg2.name)
-            ops.conv3x3_fwd([(self.A1[i], 0, 0)], reg2.w_fwd, bias(reg2.name), self.A2[i])
-            if i < L - 1:
+            pooled = ops.conv3x3_fwd([(self.A1[i], 0, 0)], reg2.w_fwd, bias(reg2.name), self.A2[i],
+                                     pool_out=self.Pool[i] if i < L - 1 else None)
+            if i < L - 1 and not pooled:
                 ops.maxpool2x2(self.A2[i], self.Pool[i])
         net = self.A2[L - 1]
         self._dec_in = []

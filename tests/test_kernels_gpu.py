@@ -492,6 +492,19 @@ def test_conv3x3_fwd_halo(ops, case):
         assert rel_err(outs[-1], ref) < 6e-3, algo
     # same products, same fp32 accumulation order over K up to the tap/chunk interleave
     assert rel_err(outs[0], outs[1]) < 3e-3
+    # fused 2x2 max pool of the same launch: bit-exact against pooling the kernel's own output
+    if ho % 2 == 0:
+        out = torch.full((n, ho, ho, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+        pool = torch.full((n, ho // 2, ho // 2, cout), -3.0, dtype=torch.bfloat16, device="cuda")
+        pooled = ops.conv3x3_fwd([(dev(x), crop, crop) for x, (_, _, crop) in zip(xs, srcs)], pack_fwd(ops, w),
+                                 dev(b, torch.float32), out, dilation=d, algo=ops.ALGO_HALO, pool_out=pool)
+        o = out.float()
+        ref_pool = o.view(n, ho // 2, 2, ho // 2, 2, cout).amax(dim=(2, 4))
+        if pooled:
+            assert torch.equal(pool.float(), ref_pool)
+        else:
+            assert float(pool.float().max()) == -3.0  # untouched: the caller runs rsu_maxpool2x2
+        assert np.array_equal(o.cpu().numpy(), outs[0])
 
 
 @pytest.mark.parametrize("case", [(2, 38, 64, 64, 1), (1, 41, 128, 64, 2), (1, 36, 64, 192, 1)])

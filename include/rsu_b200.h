@@ -228,7 +228,8 @@ int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
 int rsu_extract_patches(const float* in, int N, int H, int W, int C, int patch, int stride,
                         long long k_begin, long long k_count, float* out, void* stream);
 /* images.images_from_patches (images.py:131-164): overlap average in gather form (fp64 sums in
- * the reference's order, no atomics).  `patches` points at patch k_begin of the list; with
+ * a fixed order, no atomics; 16-byte lanes when P*C and stride*C are multiples of 4 and both
+ * pointers are 16-byte aligned).  `patches` points at patch k_begin of the list; with
  * normalize = 0 the un-divided partial sum of that slice is written (sharded prediction). */
 int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int stride,
                         long long k_begin, long long k_count, int normalize, float* out,

@@ -253,66 +253,132 @@ __global__ void __launch_bounds__(128)
 
 // images.images_from_patches (images.py:131-164) in gather form: every output pixel sums the
 // patches covering it in fp64 and divides by the hit count -- deterministic, no atomics.  A
-// pixel is covered by up to (P/stride)^2 patches (1,089 at P = 388, stride 12), far too long a
-// chain of dependent loads for one thread, so the 8 thread rows of a block each take every 8th
-// patch column (kx), issue eight loads of the inner (ky) loop together, and the 8 partial sums
-// are combined in a fixed order through shared memory.
+// pixel is covered by up to (P/stride)^2 patches (1,089 at P = 388, stride 12) that lie
+// ~600 KB apart, so the kernel is organised around which patch the whole block is reading:
+//   * a warp owns 32 x VEC consecutive elements of one output row, the 4 rows of a block are
+//     consecutive, and all of them walk the same warp-uniform (kx, ky) patch list with lanes
+//     outside a patch predicated off -- every request is one contiguous 128 x VEC byte piece
+//     of one patch row, and the block reads 4 adjacent rows of the same patch together;
+//   * the patch list is flattened and taken eight patches at a time (eight independent
+//     16-byte loads per lane in flight), the two warps that share a row take alternate groups
+//     and their partial sums are added in a fixed order through shared memory.
+// VEC = 4 needs P*C and stride*C to be multiples of 4 (every patch boundary then falls between
+// lanes and all addresses are 16-byte aligned); VEC = 1 is the general form.
 // k_lo/k_hi restrict the sum to patches whose global index (n*side*side + k) lies in
 // [k_lo, k_hi) -- a rank of a sharded prediction holds only that slice (patches points at patch
 // k_lo) and emits partial sums (normalize = 0) that are added and divided after the gather.
+template <int VEC>
 __global__ void __launch_bounds__(256)
     overlap_average_kernel(const float* __restrict__ patches, int side, int P, int C, int stride,
-                           int S, long long k_lo, long long k_hi, int normalize,
-                           float* __restrict__ out) {
-  __shared__ double part[8][32];
-  const int row = blockIdx.x;  // n*S + y
-  const int n = row / S, y = row - n * S;
-  const int row_elems = S * C;
-  const long long patch_elems = 1LL * P * P * C;
-  int ky_lo = (y - P + stride) / stride;  // ceil((y-P+1)/stride)
-  if (y - P + 1 <= 0) ky_lo = 0;
-  const int ky_hi = min(y / stride, side - 1);
-  const long long img_k0 = 1LL * n * side * side;
-  const long long ky_step = patch_elems - 1LL * stride * P * C;  // next ky: next patch, stride rows up
-  constexpr int U = 8;
-  const int xc = blockIdx.y * 32 + threadIdx.x;
-  const bool ok = xc < row_elems;
-  int kx_lo = 0, kx_hi = -1, x = 0, c = 0;
-  if (ok) {
-    x = xc / C;
-    c = xc - x * C;
-    kx_lo = (x - P + stride) / stride;
-    if (x - P + 1 <= 0) kx_lo = 0;
-    kx_hi = min(x / stride, side - 1);
-  }
-  double acc = 0.0;
-  for (int kx = kx_lo + threadIdx.y; kx <= kx_hi; kx += 8) {
-    const long long kcol = img_k0 + 1LL * kx * side;
-    // patch rows of this column that are both geometrically covering and in this rank's slice
-    const int lo = static_cast<int>(max(static_cast<long long>(ky_lo), k_lo - kcol));
-    const int hi = static_cast<int>(min(static_cast<long long>(ky_hi), k_hi - 1 - kcol));
-    if (lo > hi) continue;
-    const float* __restrict__ base =
-        patches + (kcol - k_lo) * patch_elems + (1LL * y * P + (x - kx * stride)) * C + c;
-    for (int ky0 = lo; ky0 <= hi; ky0 += U) {
-      // eight unconditional loads (indices past the end are clamped and their values dropped)
-      // so that they issue back to back: one memory latency per eight patches
-      float v[U];
-      const float* __restrict__ ptr = base + ky0 * ky_step;
+                           int S, long long total_rows, int n_chunks, long long k_lo,
+                           long long k_hi, int normalize, float* __restrict__ out) {
+  constexpr int U = 8, ROWS = 4;
+  __shared__ double part[ROWS][VEC][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = warp & (ROWS - 1), half = warp >> 2;
+  const int chunk = blockIdx.x % n_chunks;
+  const long long row = 1LL * (blockIdx.x / n_chunks) * ROWS + r;  // n*S + y
+  const int PC = P * C, sC = stride * C, row_elems = S * C;
+  const long long patch_elems = 1LL * P * PC;
+  const int xcw0 = chunk * 32 * VEC;                          // first element of the warp
+  const int xcw1 = min(xcw0 + 32 * VEC, row_elems) - 1;       // last one
+  const int xc = xcw0 + lane * VEC;
+  const bool ok = row < total_rows && xc < row_elems;
+  double acc[VEC];
 #pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = __ldg(ptr + min(u, hi - ky0) * ky_step);
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.0;
+  int cnt = 1;
+  if (row < total_rows) {
+    const int n = static_cast<int>(row / S), y = static_cast<int>(row - 1LL * n * S);
+    const long long img_k0 = 1LL * n * side * side;
+    // patches covering this row / this lane / any lane of the warp (element units along x)
+    const int ky_lo = (y - P + 1 <= 0) ? 0 : (y - P + stride) / stride;
+    const int ky_hi = min(y / stride, side - 1);
+    const int kx_lo = (xc - PC + 1 <= 0) ? 0 : (xc - PC + sC) / sC;
+    const int kx_hi = min(xc / sC, side - 1);
+    cnt = (kx_hi - kx_lo + 1) * (ky_hi - ky_lo + 1);
+    int wkx_lo = (xcw0 - PC + 1 <= 0) ? 0 : (xcw0 - PC + sC) / sC;
+    int wkx_hi = min(xcw1 / sC, side - 1);
+    // this rank's slice in image-local patch indices k = kx*side + ky, and the patch columns
+    // that can hold one of its patches
+    const long long a = k_lo - img_k0, b = k_hi - img_k0, kk = 1LL * side * side;
+    const int kl = static_cast<int>(min(max(a, 0LL), kk));
+    const unsigned kspan = static_cast<unsigned>(static_cast<int>(min(max(b, 0LL), kk)) - kl);
+    wkx_lo = max(wkx_lo, kl / side);
+    wkx_hi = kspan ? min(wkx_hi, (kl + static_cast<int>(kspan) - 1) / side) : -1;
+    // the two warps of a row split the patch columns; each walks its flattened (kx, ky) list
+    const int nky = ky_hi - ky_lo + 1, nkx = wkx_hi - wkx_lo + 1;
+    const int nkx0 = (nkx + 1) >> 1;
+    const int h_lo = half ? wkx_lo + nkx0 : wkx_lo;
+    const int h_hi = half ? wkx_hi : wkx_lo + nkx0 - 1;
+    const int total = (nky > 0 && h_hi >= h_lo) ? (h_hi - h_lo + 1) * nky : 0;
+    const int rounds = (total + U - 1) / U;
+    const int lane_lo = max(kx_lo, h_lo), lane_hi = ok ? min(kx_hi, h_hi) : -1;
+    const float* __restrict__ lane_base = patches + (1LL * y * PC + xc);
+    // element offset of patch (kx, ky) relative to lane_base, stepped incrementally:
+    // next ky = next patch, stride rows up; next kx = side patches on, stride*C elements left
+    const long long ky_step = patch_elems - 1LL * stride * PC;
+    const long long wrap_step = 1LL * side * patch_elems - sC - (nky - 1) * ky_step;
+    const int wrap_k = side - (nky - 1);
+    int kx = h_lo, ky = ky_lo, k = h_lo * side + ky_lo;
+    long long off = (img_k0 + k - k_lo) * patch_elems - (1LL * ky * stride * PC + 1LL * kx * sC);
+    // issue(): the loads of the next eight patches of the list, predicated per lane.  They are
+    // software-pipelined one group ahead of the additions, so eight to sixteen 16-byte loads
+    // per lane are always in flight (ptxas sinks a load next to its first use; here that use
+    // is one loop iteration away).
+    auto issue = [&](float (&v)[U][VEC]) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc += (ky0 + u <= hi) ? static_cast<double>(v[u]) : 0.0;
+      for (int u = 0; u < U; ++u) {
+        const bool in = kx >= lane_lo && kx <= lane_hi && static_cast<unsigned>(k - kl) < kspan;
+        if constexpr (VEC == 4) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (in) t = __ldg(reinterpret_cast<const float4*>(lane_base + off));
+          v[u][0] = t.x, v[u][1 % VEC] = t.y, v[u][2 % VEC] = t.z, v[u][3 % VEC] = t.w;
+        } else {
+          v[u][0] = in ? __ldg(lane_base + off) : 0.f;
+        }
+        const bool wrap = ky == ky_hi;
+        ky = wrap ? ky_lo : ky + 1;
+        kx += wrap ? 1 : 0;
+        k += wrap ? wrap_k : 1;
+        off += wrap ? wrap_step : ky_step;
+      }
+    };
+    auto accumulate = [&](const float (&v)[U][VEC]) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] += static_cast<double>(v[u][e]);
+    };
+    if (rounds > 0) {
+      float va[U][VEC], vb[U][VEC];
+      issue(va);
+      for (int rd = 0; rd < rounds; rd += 2) {
+        if (rd + 1 < rounds) issue(vb);
+        accumulate(va);
+        if (rd + 1 >= rounds) break;
+        if (rd + 2 < rounds) issue(va);
+        accumulate(vb);
+      }
     }
   }
-  part[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && ok) {
-    double sum = 0.0;
+  if (half == 1) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) sum += part[q][threadIdx.x];
-    const int cnt = (kx_hi - kx_lo + 1) * (ky_hi - ky_lo + 1);
-    out[1LL * row * row_elems + xc] = static_cast<float>(normalize ? sum / static_cast<double>(cnt) : sum);
+    for (int e = 0; e < VEC; ++e) part[r][e][lane] = acc[e];
+  }
+  __syncthreads();
+  if (half == 0 && ok) {
+    float res[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const double sum = acc[e] + part[r][e][lane];
+      res[e] = static_cast<float>(normalize ? sum / static_cast<double>(cnt) : sum);
+    }
+    float* __restrict__ o = out + row * row_elems + xc;
+    if constexpr (VEC == 4)
+      *reinterpret_cast<float4*>(o) = make_float4(res[0], res[1 % VEC], res[2 % VEC], res[3 % VEC]);
+    else
+      o[0] = res[0];
   }
 }
 
@@ -502,12 +568,21 @@ int rsu_overlap_average(const float* patches, int N, int side, int P, int C, int
     return set_error(RSU_EINVAL, "overlap_average: patch range outside [0, %lld)", all);
   const int S = (side - 1) * stride + P;
   const long long rows = 1LL * N * S;
-  if (rows > 0x7fffffffLL) return set_error(RSU_EINVAL, "overlap_average: more than 2^31 rows");
-  const int gy = (S * C + 31) / 32;
-  if (gy > 65535) return set_error(RSU_EINVAL, "overlap_average: row too long");
-  const dim3 grid(static_cast<unsigned>(rows), gy), block(32, 8);
-  overlap_average_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(patches, side, P, C, stride, S, k_begin,
-                                                                 k_begin + k_count, normalize, out);
+  if (1LL * P * P * C > 0x7fffffffLL || 1LL * S * C > 0x7fffffffLL || side > 46340)
+    return set_error(RSU_EINVAL, "overlap_average: patch, row or patch grid too large");
+  const bool vec = (P * C) % 4 == 0 && (stride * C) % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(patches) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int lane_elems = vec ? 4 : 1;
+  const int n_chunks = (S * C + 32 * lane_elems - 1) / (32 * lane_elems);
+  const long long blocks = ((rows + 3) / 4) * n_chunks;
+  if (blocks > 0x7fffffffLL) return set_error(RSU_EINVAL, "overlap_average: grid too large");
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (vec)
+    overlap_average_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        patches, side, P, C, stride, S, rows, n_chunks, k_begin, k_begin + k_count, normalize, out);
+  else
+    overlap_average_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        patches, side, P, C, stride, S, rows, n_chunks, k_begin, k_begin + k_count, normalize, out);
   return check_launch("overlap_average");
 }
 

@@ -86,6 +86,28 @@ def test_images_from_patches(images):
             cnt[ky * 12:ky * 12 + 388, kx * 12:kx * 12 + 388] += 1
     assert np.abs((a + b).cpu().numpy()[0, :, :, 0] / cnt - ref[0, :, :, 0]).max() <= 1e-6
     assert hits.shape == ref.shape
+    # 16-byte-lane path with channels (P*C, stride*C multiples of 4), several images, three
+    # slices that cut through patch columns and images; and the same data through the scalar
+    # path (patch pointer 4 bytes off a 16-byte boundary)
+    pc = np.random.RandomState(6).rand(3, 16, 40, 40, 3).astype(np.float32)
+    refc = IO.images_from_patches(pc.astype(np.float64), stride=8)
+    assert np.abs(images.images_from_patches(pc, stride=8) - refc).max() <= 1e-6
+    flat = torch.empty(pc.size + 1, dtype=torch.float32, device="cuda")
+    for shift in (0, 1):
+        pdc = flat[shift:shift + pc.size].view(48, 40, 40, 3)
+        pdc.copy_(torch.tensor(pc.reshape(48, 40, 40, 3)))
+        full = images.images_from_patches_dev(pdc, 3, 4, 8).cpu().numpy()
+        assert np.abs(full - refc).max() <= 1e-6
+        parts = [images.images_from_patches_dev(pdc[lo:hi], 3, 4, 8, lo, hi - lo, normalize=False)
+                 for lo, hi in ((0, 7), (7, 30), (30, 48))]
+        # the sharded pieces only line up with 16 bytes when the slice starts do; both are legal
+        hits = images.images_from_patches_dev(torch.ones_like(pdc), 3, 4, 8, normalize=False)
+        got = ((parts[0] + parts[1] + parts[2]) / hits).cpu().numpy()
+        assert np.abs(got - refc).max() <= 1e-6
+    # odd geometry (nothing divisible by 4): scalar lanes
+    po = np.random.RandomState(7).rand(2, 9, 21, 21, 1).astype(np.float32)
+    refo = IO.images_from_patches(po.astype(np.float64), stride=5)
+    assert np.abs(images.images_from_patches(po, stride=5) - refo).max() <= 1e-6
 
 
 def test_ensemble(images):

@@ -243,6 +243,17 @@ int rsu_rotate_nn_crop(const float* in, int N, int H, int C, const double* matri
 /* invert_image_augmentation_ensemble (images.py:399-417): average of the 6 un-transformed masks. */
 int rsu_ensemble_invert(const float* masks /* [6N,S,S] */, int N, int S, float* out, void* stream);
 
+/* images.quantize_mask (images.py:256-266) and the patch labels of save_submission_csv
+ * (images.py:206-237 -> extract_patches + labels_for_patches, images.py:88-99) over the
+ * patch x patch cells of N square single-channel masks (fp32 or fp64: elem_bytes 4 / 8).
+ * rule 0: label = mean(v >= pixel_threshold) > vote_threshold; rule 1: label = mean(v) >
+ * vote_threshold (fp64 means).  quantized (nullable, dtype of masks): the label written to every
+ * pixel of its cell; labels (nullable): [N][cells along x][cells along y] -- x-outer, the row
+ * order of submission.csv.  Edge cells are clipped when patch does not divide S. */
+int rsu_patch_vote(const void* masks, int elem_bytes, int N, int S, int patch, int rule,
+                   double pixel_threshold, double vote_threshold, void* quantized,
+                   unsigned char* labels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,3 +198,62 @@ def patch_f1(pred_masks, true_masks, patch_size=16, threshold=0.25):
         return 0.0
     recall, precision = tp / (tp + fn), tp / (tp + fp)
     return 2.0 / (1.0 / recall + 1.0 / precision)
+
+
+def labels_for_patches(patches, threshold=0.25):
+    """images.py:88-99 -- label 1 when the patch mean exceeds FOREGROUND_THRESHOLD."""
+    return (np.asarray(patches, np.float64).mean(axis=(1, 2)) > threshold).astype(np.int64)
+
+
+def submission_rows(masks, patch_size, threshold=0.25):
+    """images.py:206-237 -- the text of submission.csv: header, then per image one row
+    'NNN_x_y,label' per cell with x (column offset) outer and y inner; the label of cell (x, y)
+    is labels_for_patches of mask[y:y+p, x:x+p] (extract_patches order, images.py:76-77)."""
+    m = np.asarray(masks)
+    if m.ndim == 4:
+        m = m[..., 0]
+    n, s = m.shape[0], m.shape[1]
+    assert m.shape[2] == s and s % patch_size == 0
+    rows = ["id,prediction"]
+    for i in range(n):
+        for x in range(0, s, patch_size):
+            for y in range(0, s, patch_size):
+                lab = int(np.float64(m[i, y:y + patch_size, x:x + patch_size]).mean() > threshold)
+                rows.append("%03d_%d_%d,%d" % (i + 1, x, y, lab))
+    return "\n".join(rows) + "\n"
+
+
+def to_uint8(img):
+    """images.py:19-21 -- round(img * 255) as uint8."""
+    return np.round(np.asarray(img) * 255).astype(np.uint8)
+
+
+def overlays(imgs, masks, fade=0.95):
+    """images.py:102-128 -- red layer (255, 0, 0, trunc(uint8(mask) * fade)) composited over the
+    opaque image with Pillow's integer 'over' operator (Image.alpha_composite): per channel
+    out = (src * a + dst * (255 - a) + rounding) / 255 on 8-bit values, alpha stays 255."""
+    base = to_uint8(imgs).astype(np.int64)
+    a = (to_uint8(np.asarray(masks).reshape(base.shape[:3])) * fade).astype(np.uint8).astype(np.int64)
+    out = np.empty(base.shape[:3] + (4,), np.uint8)
+    src = np.array([255, 0, 0], np.int64)
+    # Pillow's composite for an opaque destination: blend = a * 255 (outA = 255*255 scale),
+    # coef1 = a * 255 * 255 / outA255, ... reduces to the rounded 8-bit lerp below
+    for c in range(3):
+        t = src[c] * a[..., None][..., 0] + base[..., c] * (255 - a) + 128
+        out[..., c] = ((t + (t >> 8)) >> 8).astype(np.uint8)
+    out[..., 3] = 255
+    return out
+
+
+def overlap_pred_true(pred, true):
+    """images.py:284-294 -- R = uint8(pred), G = uint8(true), B = 0."""
+    out = np.zeros(np.asarray(pred).shape + (3,), np.uint8)
+    out[..., 0] = to_uint8(pred)
+    out[..., 1] = to_uint8(true)
+    return out
+
+
+def overlapp_error(pred, true):
+    """images.py:297-310 -- 255 on all channels where (uint8(pred) != 0) == (uint8(true) != 0)."""
+    agree = (to_uint8(pred) != 0) == (to_uint8(true) != 0)
+    return np.repeat((agree.astype(np.uint8) * 255)[..., None], 3, axis=-1)

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "rsu_overlap_average": (_i, [_vp, _i, _i, _i, _i, _i, _ll, _ll, _i, _vp, _vp]),
     "rsu_rotate_nn_crop": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _i, _i, _vp, _vp]),
     "rsu_ensemble_invert": (_i, [_vp, _i, _i, _vp, _vp]),
+    "rsu_patch_vote": (_i, [_vp, _i, _i, _i, _i, _i, C.c_double, C.c_double, _vp, _vp, _vp]),
 }
 EXPORTS = sorted(_SIGNATURES)
 

@@ -8,12 +8,14 @@ the GPU.  Pure data movement (mirror, flips, rot90, crops, patches, nearest-neig
 is bit-exact for float32 and float64 inputs (float64 moves as pairs of 32-bit words); the two
 averaging helpers accumulate in fp64 on the device from fp32 inputs.
 
-The I/O and visualisation helpers of the reference (load, overlays, save_all, ...) are out of
-scope; the small NumPy post-processing rules needed to score a prediction
-(quantize_mask, labels_for_patches, img_float_to_uint8, predictions_to_patches) are kept as host
-code.
+The scoring rules (quantize_mask, labels_for_patches, the label grid of save_submission_csv)
+run the `rsu_patch_vote` kernel; the PNG / CSV helpers around the path (load, save_all, overlays,
+overlap_pred_true, overlapp_error, save_submission_csv -- SURVEY.md section 8(f)) are host code
+on PIL, without matplotlib.
 """
 import ctypes as C
+import glob
+import os
 
 import numpy as np
 import torch
@@ -262,27 +264,205 @@ def invert_image_augmentation_ensemble(masks):
     return out[..., None] if has_c else out
 
 
-# ------------------------------------------------------------------ host-side scoring rules
+# ------------------------------------------------------------------ scoring rules (device)
+RULE_VOTE, RULE_MEAN = 0, 1
+
+
+def patch_vote_dev(masks, patch_size, rule, vote_threshold, pixel_threshold=0.5, quantized=False,
+                   labels=True):
+    """masks: float32 / float64 CUDA [N,S,S] -> (quantized masks or None, uint8 labels
+    [N, cells_x, cells_y] or None).  rule RULE_VOTE = quantize_mask's 'mean(v >= 0.5) > t',
+    RULE_MEAN = labels_for_patches' 'mean(v) > t'."""
+    assert masks.dim() == 3 and masks.shape[1] == masks.shape[2], "square single-channel masks"
+    assert masks.dtype in (torch.float32, torch.float64)
+    masks = masks.contiguous()
+    N, S = masks.shape[0], masks.shape[1]
+    g = -(-S // patch_size)
+    q = torch.empty_like(masks) if quantized else None
+    lab = torch.empty(N, g, g, dtype=torch.uint8, device=masks.device) if labels else None
+    call("rsu_patch_vote", _ptr(masks), masks.element_size(), N, S, int(patch_size), int(rule),
+         float(pixel_threshold), float(vote_threshold), _ptr(q) if quantized else None,
+         _ptr(lab) if labels else None)
+    return q, lab
+
+
+def _masks_to_dev(masks):
+    m = np.ascontiguousarray(masks)
+    if m.dtype not in (np.float32, np.float64):
+        m = m.astype(np.float64)
+    has_c = m.ndim == 4
+    assert not has_c or m.shape[3] == 1, "masks have one channel"
+    return torch.from_numpy(m.reshape(m.shape[0], m.shape[1], m.shape[2])).cuda(), has_c
+
+
 def labels_for_patches(patches):
-    """label 1 = road when the patch mean exceeds FOREGROUND_THRESHOLD (images.py:88-99)"""
-    foreground = patches.mean(axis=(1, 2)) > FOREGROUND_THRESHOLD
-    return foreground.astype(np.int64)
+    """label 1 = road when the patch mean exceeds FOREGROUND_THRESHOLD (images.py:88-99);
+    patches [num, p, p] -> int64 [num]"""
+    t, _ = _masks_to_dev(patches)
+    _, lab = patch_vote_dev(t, t.shape[1], RULE_MEAN, FOREGROUND_THRESHOLD)
+    return lab.reshape(-1).cpu().numpy().astype(np.int64)
 
 
 def predictions_to_patches(predictions, patch_size):
     """Expand each prediction to a square patch (images.py:167-180)"""
-    num_predictions = predictions.shape[0]
-    predictions = np.resize(predictions, (num_predictions, 1, 1, 1))
-    return np.broadcast_to(predictions, (num_predictions, patch_size, patch_size, 1))
+    flat = np.asarray(predictions).reshape(-1)
+    return np.broadcast_to(flat[:, None, None, None], (flat.shape[0], patch_size, patch_size, 1))
 
 
 def quantize_mask(masks, threshold, patch_size):
-    """patch_size x patch_size vote: mean(prob >= 0.5) > threshold (images.py:256-266)"""
-    num_images, img_size, _, _ = masks.shape
-    quantized_masks = masks.copy()
+    """patch_size x patch_size vote: mean(prob >= 0.5) > threshold, written back to every pixel
+    of the cell (images.py:256-266); [N,S,S,1] in, same shape and dtype out"""
+    t, has_c = _masks_to_dev(masks)
+    q, _ = patch_vote_dev(t, patch_size, RULE_VOTE, threshold, quantized=True, labels=False)
+    out = q.cpu().numpy()
+    return out[..., None] if has_c else out
+
+
+def patch_labels(masks, patch_size, threshold=FOREGROUND_THRESHOLD, rule=RULE_MEAN):
+    """Label grid of a batch of masks: int64 [N, cells, cells] indexed [image, x cell, y cell] --
+    what save_submission_csv derives through extract_patches + labels_for_patches
+    (images.py:218-224)."""
+    t, _ = _masks_to_dev(masks)
+    assert t.shape[1] % patch_size == 0, "Stride sliding should cover the whole image"
+    _, lab = patch_vote_dev(t, patch_size, rule, threshold)
+    return lab.cpu().numpy().astype(np.int64)
+
+
+def patch_scores(pred_labels, true_labels):
+    """accuracy, recall, precision, F1 = 2 / (1/recall + 1/precision) over patch labels
+    (summary.py:141-147)."""
+    p = np.asarray(pred_labels).reshape(-1) > 0
+    t = np.asarray(true_labels).reshape(-1) > 0
+    tp, fp, fn = float(np.sum(p & t)), float(np.sum(p & ~t)), float(np.sum(~p & t))
+    accuracy = float(np.mean(p == t))
+    recall = tp / (tp + fn) if tp + fn > 0 else 0.0
+    precision = tp / (tp + fp) if tp + fp > 0 else 0.0
+    f1 = 2.0 / (1.0 / recall + 1.0 / precision) if recall > 0 and precision > 0 else 0.0
+    return accuracy, recall, precision, f1
+
+
+def save_submission_csv(masks, path, patch_size):
+    """Save the masks in the expected format for submission (images.py:206-237): one row
+    'NNN_x_y,label' per patch_size cell, image-major, x outer, y inner."""
+    masks = np.asarray(masks)
+    if masks.ndim == 4:
+        masks = masks.squeeze(-1)
+    num_mask, mask_height, mask_width = masks.shape
+    assert mask_height == mask_width, "images should be square"
+    labels = patch_labels(masks, patch_size)
+    os.makedirs(path, exist_ok=True)
+    filename = os.path.abspath(os.path.join(path, "submission.csv"))
+    print("Saving predictions in {}".format(filename))
+    cells = np.arange(labels.shape[1]) * patch_size
+    rows = ["id,prediction"]
+    for n in range(num_mask):
+        rows.extend("{:03d}_{}_{},{}".format(n + 1, x, y, labels[n, j, i])
+                    for j, x in enumerate(cells) for i, y in enumerate(cells))
+    with open(filename, "w") as f:
+        f.write("\n".join(rows) + "\n")
+    print("Done")
+
+
+# ------------------------------------------------------------------ image files and visual dumps
+def _png_to_float(img):
+    """PIL image -> float32 array in [0, 1] with matplotlib.image.imread's PNG conventions
+    (8-bit / 255, 16-bit / 65535, palettes expanded, channels kept)."""
+    if img.mode == "P":
+        img = img.convert("RGBA" if "transparency" in img.info else "RGB")
+    if img.mode in ("I;16", "I;16B", "I;16L", "I"):
+        return (np.asarray(img, dtype=np.float64) / 65535.0).astype(np.float32)
+    if img.mode == "1":
+        img = img.convert("L")
+    return np.asarray(img, dtype=np.float32) / np.float32(255.0)
+
+
+def load(directory):
+    """Extract the images in `directory` into a tensor [num_images, height, width(, channels)]
+    (images.py:24-32), float32 in [0, 1], files in sorted order"""
+    from PIL import Image
+    print('Loading images from {} ...'.format(directory))
+    files = sorted(glob.glob(os.path.join(directory, '*.png')))
+    loaded = []
+    for file_path in files:
+        with Image.open(file_path) as img:
+            loaded.append(_png_to_float(img))
+    print("Loaded {} images from {}".format(len(loaded), directory))
+    return np.asarray(loaded)
+
+
+def load_train_data(directory):
+    """images of `directory`/images and masks of `directory`/groundtruth (images.py:240-253)"""
+    return (load(os.path.abspath(os.path.join(directory, 'images/'))),
+            load(os.path.abspath(os.path.join(directory, 'groundtruth/'))))
+
+
+def overlays(imgs, masks, fade=0.95):
+    """Add the masks on top of the images with red transparency (images.py:102-128):
+    RGBA uint8 [N,H,W,4]; the red layer's alpha is uint8(mask) * fade, truncated."""
+    from PIL import Image
+    num_images, im_height, im_width, num_channel = imgs.shape
+    assert num_channel == 3, 'Predict image should be colored'
+    base = img_float_to_uint8(imgs)
+    alpha = (img_float_to_uint8(np.asarray(masks).reshape(num_images, im_height, im_width)) * fade).astype(np.uint8)
+    red = np.zeros((im_height, im_width, 4), dtype=np.uint8)
+    red[..., 0] = 255
+    out = np.empty((num_images, im_height, im_width, 4), dtype=np.uint8)
     for n in range(num_images):
-        for y in range(0, img_size, patch_size):
-            for x in range(0, img_size, patch_size):
-                label = (masks[n, y:y + patch_size, x:x + patch_size, 0] >= 0.5).mean() > threshold
-                quantized_masks[n, y:y + patch_size, x:x + patch_size, 0] = label
-    return quantized_masks
+        red[..., 3] = alpha[n]
+        out[n] = np.asarray(Image.alpha_composite(Image.fromarray(base[n]).convert('RGBA'),
+                                                  Image.fromarray(red)))
+    return out
+
+
+def overlap_pred_true(pred, true):
+    """confusion image: prediction in the red channel, ground truth in the green one
+    (images.py:284-294)"""
+    stacked = np.zeros(pred.shape + (3,), dtype=np.uint8)
+    stacked[..., 0] = img_float_to_uint8(pred)
+    stacked[..., 1] = img_float_to_uint8(true)
+    return stacked
+
+
+def overlapp_error(pred, true):
+    """white where thresholded prediction and ground truth agree, black where they differ
+    (images.py:297-310; 'agree' = both zero or both non-zero after the uint8 conversion)"""
+    agree = (img_float_to_uint8(true) != 0) == (img_float_to_uint8(pred) != 0)
+    return np.repeat((agree * np.uint8(PIXEL_DEPTH))[..., None], 3, axis=-1)
+
+
+def _grey_bytes(img):
+    """matplotlib 2.1's imsave of a 2-D array with cmap='gray' (requirements.txt:6; matplotlib is
+    absent here, so this follows its published Normalize + Colormap.__call__(bytes=True)): min/max
+    normalisation, index int(v * 256) into a 256-entry linear table whose byte form is
+    (linspace(0, 1, 256) * 255) truncated."""
+    a = np.asarray(img, dtype=np.float64)
+    lo, hi = float(a.min()), float(a.max())
+    norm = np.zeros_like(a) if hi == lo else (a - lo) / (hi - lo)
+    table = (np.linspace(0.0, 1.0, 256) * 255).astype(np.uint8)
+    return table[np.minimum((norm * 256).astype(np.int64), 255)]
+
+
+def save_all(images, directory, format_="images_{:03d}.png", greyscale=False):
+    """Save the `images` in the `directory` as RGBA PNG files numbered from 1
+    (images.py:183-203).  2-D images need greyscale=True (matplotlib's default colour map is not
+    reproduced); float RGB(A) images must lie in [0, 1]."""
+    from PIL import Image
+    os.makedirs(directory, exist_ok=True)
+    images = np.asarray(images)
+    if images.ndim == 4 and images.shape[-1] == 1:
+        images = images.squeeze(-1)
+    for n in range(images.shape[0]):
+        img = images[n]
+        if img.ndim == 2:
+            if not greyscale:
+                raise NotImplementedError("save_all: 2-D images are only written with greyscale=True")
+            g = _grey_bytes(img)
+            rgba = np.stack([g, g, g, np.full_like(g, 255)], axis=-1)
+        else:
+            if img.dtype != np.uint8:
+                if img.min() < 0 or img.max() > 1:
+                    raise ValueError("Floating point image RGB values must be in the 0..1 range.")
+                img = (img * 255).astype(np.uint8)
+            rgba = img if img.shape[-1] == 4 else np.concatenate(
+                [img, np.full(img.shape[:2] + (1,), 255, np.uint8)], axis=-1)
+        Image.fromarray(np.ascontiguousarray(rgba), "RGBA").save(os.path.join(directory, format_.format(n + 1)))

@@ -439,8 +439,13 @@ class ConvolutionalModel:
         marker the reference's restore() globs for); all variables incl. momentum slots,
         global_step and the dead conv_dilut_{L-1} weights, keyed by TensorFlow variable names."""
         opts = self._options
-        model_data_dir = os.path.abspath(
-            os.path.join(opts.save_path, self.experiment_name, 'model-epoch-{:03d}.chkpt'.format(epoch)))
+        return self.save_to(os.path.abspath(
+            os.path.join(opts.save_path, self.experiment_name, 'model-epoch-{:03d}.chkpt'.format(epoch))))
+
+    def save_to(self, model_data_dir):
+        """The checkpoint write behind save(); also used for the '<save_dir>-model.chkpt' copy
+        of a submission run (tf_aerial_images.py:461)."""
+        opts = self._options
         if self._dist.rank == 0:
             os.makedirs(os.path.dirname(model_data_dir), exist_ok=True)
             payload = {}
@@ -511,7 +516,7 @@ def main(argv=None):
             model.restore(date=opts.restore_date, epoch=opts.restore_epoch)
 
     if opts.num_epoch > 0:
-        train_images, train_groundtruth = load_train_data(opts.train_data_dir)
+        train_images, train_groundtruth = images.load_train_data(opts.train_data_dir)
 
         input_size = unet.input_size_needed(opts.patch_size, opts.num_layers)
         offset = int((input_size - opts.patch_size) / 2)
@@ -536,31 +541,40 @@ def main(argv=None):
             model.train(patches, labels_patches, train_images, train_groundtruth)  # Process one epoch
             model.save(i)  # Save model to disk
 
+    if opts.eval_train:
+        # dump predictions on the training set (tf_aerial_images.py:432-446)
+        print("Evaluate Test")
+        eval_images, eval_groundtruth = images.load_train_data(opts.train_data_dir)
+        pred_masks = model.predict_batchwise(eval_images, opts.pred_batch_size)
+        pred_labels = ((pred_masks > 0.5) * 1).squeeze(-1)
+        dumps = (
+            (pred_labels, "eval_binary_pred_{:03d}.png", True),
+            (pred_masks, "eval_probability_pred_{:03d}.png", True),
+            (images.overlays(eval_images, pred_masks, fade=0.5), "eval_overlays_pred_{:03d}.png", False),
+            (images.overlap_pred_true(pred_labels, eval_groundtruth), "eval_confusion_{:03d}.png", False),
+            (images.overlapp_error(pred_labels, eval_groundtruth), "eval_orror_{:03d}.png", True),
+        )
+        for arrays, name, grey in dumps:
+            images.save_all(arrays, opts.eval_data_dir, name, greyscale=grey)
+
     if opts.eval_data_dir and not opts.eval_train:
+        # submission run (tf_aerial_images.py:448-461): masks -> 16 x 16 vote -> overlays + csv
         print("Running inference on eval data {}".format(opts.eval_data_dir))
-        eval_images = load_images(opts.eval_data_dir)
+        eval_images = images.load(opts.eval_data_dir)
         start = time.time()
         masks = model.predict_batchwise(eval_images, opts.pred_batch_size)
         stop = time.time()
         print("Prediction time:{} mins".format((stop - start) / 60))
         masks = images.quantize_mask(masks, patch_size=IMG_PATCH_SIZE, threshold=FOREGROUND_THRESHOLD)
-        np.save(os.path.join(opts.save_path, model.experiment_name + "-masks.npy"), masks)
+        save_dir = os.path.abspath(os.path.join(opts.save_path, model.experiment_name))
+        images.save_all(images.overlays(eval_images, masks, fade=0.4), save_dir)
+        images.save_submission_csv(masks, save_dir, IMG_PATCH_SIZE)
+        model.save_to(save_dir + "-model.chkpt")  # the model used for the submission
     return model
 
 
-def load_images(directory):
-    """PNG directory -> float32 [N,H,W(,C)] in [0,1] (images.load, images.py:24-32) via PIL."""
-    from PIL import Image
-    out = []
-    for file_path in sorted(glob.glob(os.path.join(directory, '*.png'))):
-        out.append(np.asarray(Image.open(file_path), dtype=np.float32) / 255.0)
-    return np.asarray(out)
-
-
-def load_train_data(directory):
-    """images.load_train_data (images.py:240-253)."""
-    return (load_images(os.path.abspath(os.path.join(directory, 'images/'))),
-            load_images(os.path.abspath(os.path.join(directory, 'groundtruth/'))))
+load_images = images.load                    # kept under their earlier names
+load_train_data = images.load_train_data
 
 
 if __name__ == '__main__':

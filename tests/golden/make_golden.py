@@ -72,6 +72,30 @@ def main():
     # quantize_mask (images.py:256-266)
     qm = rs.rand(2, 32, 32, 1)
     g["quant_in"], g["quant_out"] = qm, ref.quantize_mask(qm, threshold=0.25, patch_size=16)
+    # scoring rules and visual dumps (images.py:88-128, 167-180, 206-237, 284-310)
+    lp = rs.rand(10, 16, 16) * 0.5
+    g["labels_in"], g["labels_out"] = lp, ref.labels_for_patches(lp)
+    g["pred_to_patches_in"] = np.arange(5)
+    g["pred_to_patches_out"] = np.ascontiguousarray(ref.predictions_to_patches(np.arange(5), 4))
+    oi = rs.rand(2, 12, 12, 3).astype(np.float32)
+    om = rs.rand(2, 12, 12, 1)
+    g["overlay_img"], g["overlay_mask"] = oi, om
+    g["overlay_out_095"] = ref.overlays(oi, om)
+    g["overlay_out_040"] = ref.overlays(oi, om, fade=0.4)
+    pb, tb = (rs.rand(2, 12, 12) > 0.5) * 1, (rs.rand(2, 12, 12) > 0.5) * 1.0
+    g["confusion_pred"], g["confusion_true"] = pb, tb
+    g["confusion_out"] = ref.overlap_pred_true(pb, tb)
+    g["error_out"] = ref.overlapp_error(pb, tb)
+    import tempfile
+    qd = ref.quantize_mask(rs.rand(2, 48, 48, 1), threshold=0.25, patch_size=16)
+    with tempfile.TemporaryDirectory() as td:
+        ref.save_submission_csv(qd, td, 16)
+        with open(os.path.join(td, "submission.csv"), "rb") as f:
+            g["csv_in"], g["csv_text"] = qd, np.frombuffer(f.read(), dtype=np.uint8)
+    # the first rows of one of the reference's own submission files pin the on-disk format
+    sub = sorted(os.listdir("/root/reference/submissions"))[0]
+    with open(os.path.join("/root/reference/submissions", sub, "submission.csv"), "rb") as f:
+        g["csv_reference_head"] = np.frombuffer(b"".join(f.readlines()[:40]), dtype=np.uint8)
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(g), "arrays")
 

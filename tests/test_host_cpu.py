@@ -82,18 +82,48 @@ def test_input_size_and_flops():
     assert all(np.array_equal(a[k], b[k]) for k in a)
 
 
-def test_host_scoring_rules():
-    """quantize_mask / labels_for_patches keep the reference rules (images.py:88-99, 256-266)."""
+def test_host_visual_and_io_helpers(tmp_path):
+    """The host-side helpers around the path against goldens made by
+    the reference's own images.py: overlays, confusion / error images, predictions_to_patches,
+    patch scores, PNG save -> load round trip.  (The device scoring rules are GPU tests.)"""
     from road_segmentation_unet_b200 import images
     from oracle import images_oracle as IO
     G = np.load(os.path.join(ROOT, "tests", "golden", "images_golden.npz"))
-    assert np.array_equal(images.quantize_mask(G["quant_in"], 0.25, 16), G["quant_out"])
-    p = np.zeros((3, 4, 4))
-    p[1] = 1.0
-    p[2, :1] = 1.0  # mean 0.25 is NOT > 0.25
-    assert images.labels_for_patches(p).tolist() == [0, 1, 0]
+    assert np.array_equal(images.overlays(G["overlay_img"], G["overlay_mask"]), G["overlay_out_095"])
+    assert np.array_equal(images.overlays(G["overlay_img"], G["overlay_mask"], fade=0.4), G["overlay_out_040"])
+    assert np.array_equal(images.overlap_pred_true(G["confusion_pred"], G["confusion_true"]), G["confusion_out"])
+    assert np.array_equal(images.overlapp_error(G["confusion_pred"], G["confusion_true"]), G["error_out"])
+    assert np.array_equal(images.predictions_to_patches(G["pred_to_patches_in"], 4), G["pred_to_patches_out"])
     assert images.predictions_to_patches(np.array([0, 1]), 2).shape == (2, 2, 2, 1)
     assert IO.patch_f1(G["quant_in"], G["quant_in"]) == 1.0
+    # accuracy / recall / precision / F1 of summary.py:141-147
+    acc, rec, prec, f1 = images.patch_scores([1, 1, 0, 0, 1], [1, 0, 0, 1, 1])
+    assert (acc, rec, prec) == (0.6, 2 / 3, 2 / 3) and abs(f1 - 2 / 3) < 1e-12
+    assert images.patch_scores([0, 0], [0, 1])[3] == 0.0
+    # PNG round trip: RGB float, RGBA overlays, greyscale masks (min/max normalised like imsave)
+    rgb = np.random.RandomState(0).randint(0, 256, (2, 6, 6, 3)).astype(np.uint8)
+    images.save_all(rgb.astype(np.float32) / 255, str(tmp_path / "rgb"))
+    back = images.load(str(tmp_path / "rgb"))
+    assert back.dtype == np.float32 and back.shape == (2, 6, 6, 4)
+    assert np.array_equal(images.img_float_to_uint8(back[..., :3]), rgb) and np.all(back[..., 3] == 1)
+    assert sorted(os.listdir(tmp_path / "rgb")) == ["images_001.png", "images_002.png"]
+    images.save_all(G["overlay_out_095"], str(tmp_path / "ov"), "o_{:03d}.png")
+    assert np.array_equal(images.img_float_to_uint8(images.load(str(tmp_path / "ov"))), G["overlay_out_095"])
+    binary = (np.random.RandomState(1).rand(1, 8, 8, 1) > 0.5) * 1
+    images.save_all(binary, str(tmp_path / "bin"), "b_{:03d}.png", greyscale=True)
+    grey = images.load(str(tmp_path / "bin"))
+    assert np.array_equal(grey[0, :, :, 0], binary[0, :, :, 0].astype(np.float32))
+    with pytest.raises(NotImplementedError):
+        images.save_all(binary, str(tmp_path / "bin"))
+    # greyscale groundtruth-style file -> 2-D float32 in [0, 1]
+    from PIL import Image
+    os.makedirs(tmp_path / "gt" / "groundtruth")
+    os.makedirs(tmp_path / "gt" / "images")
+    Image.fromarray(rgb[0, :, :, 0], "L").save(tmp_path / "gt" / "groundtruth" / "a.png")
+    Image.fromarray(rgb[0], "RGB").save(tmp_path / "gt" / "images" / "a.png")
+    im, gt = images.load_train_data(str(tmp_path / "gt"))
+    assert im.shape == (1, 6, 6, 3) and gt.shape == (1, 6, 6)
+    assert np.array_equal(gt[0], rgb[0, :, :, 0].astype(np.float32) / np.float32(255))
 
 
 def test_shard_helpers():

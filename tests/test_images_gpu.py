@@ -168,3 +168,39 @@ def test_expand_and_rotate(images):
     ref = IO.expand_and_rotate(x, [15, 45, 75], 188)
     assert got.shape == (3, 776, 776, 3)
     assert float((got != ref).any(axis=-1).mean()) == 0.0
+
+
+def test_scoring_rules(images, tmp_path):
+    """rsu_patch_vote behind quantize_mask / labels_for_patches / save_submission_csv
+    (images.py:88-99, 206-237, 256-266): bit-exact against the reference's own outputs."""
+    for dt in (np.float64, np.float32):
+        q = images.quantize_mask(G["quant_in"].astype(dt), 0.25, 16)
+        assert q.dtype == dt and q.shape == G["quant_in"].shape
+        assert np.array_equal(q, G["quant_out"].astype(dt) if dt == np.float32 else G["quant_out"])
+    # a value just below 0.5 in fp64 must not be rounded up through fp32
+    edge = np.full((1, 16, 16, 1), np.nextafter(0.5, 0.0))
+    assert images.quantize_mask(edge, 0.25, 16).max() == 0.0
+    assert images.quantize_mask(edge.astype(np.float32), 0.25, 16).min() == 1.0
+    # cells clipped at the border when the patch size does not divide the image (reference slices)
+    odd = np.random.RandomState(8).rand(2, 40, 40, 1)
+    assert np.array_equal(images.quantize_mask(odd, 0.25, 16), IO.quantize_mask(odd, 0.25, 16))
+    assert np.array_equal(images.labels_for_patches(G["labels_in"]), G["labels_out"])
+    p = np.zeros((3, 4, 4))
+    p[1] = 1.0
+    p[2, :1] = 1.0  # mean 0.25 is NOT > 0.25
+    assert images.labels_for_patches(p).tolist() == [0, 1, 0]
+    # label grid [image, x cell, y cell] and the csv text
+    lab = images.patch_labels(G["csv_in"], 16)
+    want = np.array([[[G["csv_in"][n, y:y + 16, x:x + 16, 0].mean() > 0.25 for y in range(0, 48, 16)]
+                      for x in range(0, 48, 16)] for n in range(2)])
+    assert lab.dtype == np.int64 and np.array_equal(lab, want)
+    images.save_submission_csv(G["csv_in"], str(tmp_path / "sub"), 16)
+    with open(tmp_path / "sub" / "submission.csv", "rb") as f:
+        assert f.read() == bytes(G["csv_text"])
+    # 608^2 masks -> 38 x 38 labels per image, vote rule == patch F1 of the oracle
+    rs = np.random.RandomState(9)
+    pm, tm = rs.rand(3, 608, 608, 1).astype(np.float32), (rs.rand(3, 608, 608, 1) > 0.4) * 1.0
+    lp = images.patch_labels(pm, 16, rule=images.RULE_VOTE)
+    lt = images.patch_labels(tm, 16, rule=images.RULE_VOTE)
+    assert lp.shape == (3, 38, 38)
+    assert abs(images.patch_scores(lp, lt)[3] - IO.patch_f1(pm, tm)) < 1e-12

@@ -88,6 +88,22 @@ def test_quantize_golden():
 
 
 # ------------------------------------------------------------------ U-Net oracle
+def test_scoring_and_visual_golden():
+    """labels, submission.csv text, overlays, confusion / error images."""
+    assert np.array_equal(IO.labels_for_patches(G["labels_in"]), G["labels_out"])
+    assert IO.submission_rows(G["csv_in"], 16) == bytes(G["csv_text"]).decode()
+    for fade, key in ((0.95, "overlay_out_095"), (0.4, "overlay_out_040")):
+        assert np.array_equal(IO.overlays(G["overlay_img"], G["overlay_mask"], fade), G[key])
+    assert np.array_equal(IO.overlap_pred_true(G["confusion_pred"], G["confusion_true"]), G["confusion_out"])
+    assert np.array_equal(IO.overlapp_error(G["confusion_pred"], G["confusion_true"]), G["error_out"])
+    # the on-disk format of the reference's own submissions/*/submission.csv
+    head = bytes(G["csv_reference_head"]).decode().splitlines()
+    assert head[0] == "id,prediction"
+    assert [r.split(",")[0] for r in head[1:]] == ["001_0_%d" % (16 * i) for i in range(38)] + ["001_16_0"]
+    assert IO.submission_rows(np.zeros((1, 608, 608)), 16).splitlines()[:40] == \
+        [head[0]] + [r.split(",")[0] + ",0" for r in head[1:]]
+
+
 def test_input_size_needed():
     """unet.py:100-115; closed form S = P + 12 * 2^(L-1) - 8 (report/report.tex:50)."""
     assert UO.input_size_needed(388, 4) == 476

@@ -175,3 +175,44 @@ def test_prefetch_is_transparent(tmp_path):
     assert a.prefetch(*pinned[2]) is False
     a.train_batch(*pinned[2])  # not staged: drops the stale entries and stages synchronously
     assert a.train_batch(*pinned[0])[0] > 0
+
+
+def test_main_train_eval_submission(tmp_path):
+    """The command-line flow of tf_aerial_images.main (tf_aerial_images.py:382-461) on PNG files:
+    train one epoch, dump the training-set evaluation images, then a submission run that writes
+    overlays, submission.csv and the model copy."""
+    from PIL import Image
+    from road_segmentation_unet_b200 import images, tf_aerial_images as tfa
+    rs = np.random.RandomState(11)
+    imgs, labs = make_data(rs, 4, 48)
+    for sub in ("train/images", "train/groundtruth", "test"):
+        (tmp_path / sub).mkdir(parents=True)
+    for i in range(4):
+        Image.fromarray(images.img_float_to_uint8(imgs[i]), "RGB").save(tmp_path / "train/images" / ("s_%02d.png" % i))
+        Image.fromarray(images.img_float_to_uint8(labs[i]), "L").save(tmp_path / "train/groundtruth" / ("s_%02d.png" % i))
+        Image.fromarray(images.img_float_to_uint8(imgs[i]), "RGB").save(tmp_path / "test" / ("t_%02d.png" % i))
+    common = ["--num_layers=3", "--dilated_layers", "--patch_size=36", "--batch_size=4", "--stride=12",
+              "--dropout=1.0", "--gpu=0", "--seed=3", "--pred_batch_size=2",
+              "--save_path=" + str(tmp_path / "runs"), "--train_data_dir=" + str(tmp_path / "train")]
+    model = tfa.main(common + ["--num_epoch=1", "--rotation_angles=0,90", "--eval_train",
+                               "--eval_data_dir=" + str(tmp_path / "dump")])
+    names = sorted(p.name for p in (tmp_path / "dump").iterdir())
+    assert len(names) == 20 and names[0] == "eval_binary_pred_001.png" and "eval_orror_004.png" in names
+    conf = images.load(str(tmp_path / "dump"))  # all five dumps are RGBA files of the image size
+    assert conf.shape == (20, 48, 48, 4)
+    run_dir = tmp_path / "runs" / model.experiment_name
+    assert (run_dir / "model-epoch-000.chkpt").exists()
+
+    model2 = tfa.main(common + ["--num_epoch=0", "--restore_model", "--eval_data_dir=" + str(tmp_path / "test")])
+    out_dir = tmp_path / "runs" / model2.experiment_name
+    rows = (out_dir / "submission.csv").read_text().splitlines()
+    assert rows[0] == "id,prediction" and len(rows) == 1 + 4 * 9
+    assert rows[1].startswith("001_0_0,") and rows[4].startswith("001_16_0,") and rows[-1].startswith("004_32_32,")
+    assert sorted(p.name for p in out_dir.glob("images_*.png")) == ["images_%03d.png" % i for i in range(1, 5)]
+    assert (tmp_path / "runs" / (model2.experiment_name + "-model.chkpt")).exists()
+    # the restored model predicts what the trained one does, and the csv carries the 16 x 16 vote
+    test_imgs = images.load(str(tmp_path / "test"))
+    masks = model2.predict_batchwise(test_imgs, 2)
+    assert np.abs(masks - model.predict_batchwise(test_imgs, 2)).max() == 0.0
+    lab = images.patch_labels(images.quantize_mask(masks, 0.25, 16), 16)
+    assert [int(r.split(",")[1]) for r in rows[1:]] == lab.reshape(-1).tolist()

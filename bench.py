@@ -283,26 +283,50 @@ def run_gpu(args):
         import io
         opts.ensemble_prediction, opts.stride = True, 12
         imgs = np.random.RandomState(2017).rand(args.predict_images, 604, 604, 3).astype(np.float32)
-        with contextlib.redirect_stdout(io.StringIO()):
-            model.predict(imgs[:, :400, :400])  # warm-up on a small crop (4 patches per variant)
-            barrier()
-            t0 = time.perf_counter()
-            masks = model.predict(imgs)
-            torch.cuda.synchronize()
-            pred_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([pred_s], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            pred_s = float(t.item())
+
+        def timed_predict(shared, warm):
+            opts.shared_windows = shared
+            with contextlib.redirect_stdout(io.StringIO()):
+                model.predict(warm)
+                barrier()
+                t0 = time.perf_counter()
+                out = model.predict(imgs)
+                torch.cuda.synchronize()
+                sec = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([sec], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec = float(t.item())
+            return out, sec
+
+        def flops(patch):
+            return sum(unet.plan_flops(CFG["num_layers"], CFG["root_size"], CFG["dilated_layers"], patch).values())
+
+        mpix = args.predict_images * 604 * 604 / 1e6
+        # (a) the reference's loop: one forward pass per sliding window (2,166 per image)
+        masks_loop, loop_s = timed_predict(False, imgs[:, :400, :400])  # warm-up: 4 patches per variant
         n_fwd = args.predict_images * 6 * 19 * 19
-        f_fwd = sum(unet.plan_flops(CFG["num_layers"], CFG["root_size"], CFG["dilated_layers"],
-                                    CFG["patch_size"]).values())
-        predict = {"value": masks.shape[0] * masks.shape[1] * masks.shape[2] / pred_s / 1e6,
-                   "unit": "Mpix/s", "seconds": pred_s, "patch_forwards_per_s": n_fwd / pred_s,
-                   "tflops": n_fwd * f_fwd / pred_s / 1e12,
-                   "config": "%d synthetic 604^2 image(s), stride 12, 6-way ensemble, %d patch forwards "
-                             "sharded over %d GPU(s), ConvolutionalModel.predict (host in / host out)"
-                             % (args.predict_images, n_fwd, world),
+        # (b) the default path: windows whose origins differ by a multiple of the pooling period
+        # are evaluated once inside an enlarged window (tf_aerial_images.shared_window_plan)
+        masks, pred_s = timed_predict(True, imgs)  # warm-up allocates the enlarged engine
+        n_big, q_big, wins = tfa.shared_window_plan(19, 12, S, CFG["num_layers"], opts.shared_window_max_input)
+        n_win = args.predict_images * 6 * len(wins) ** 2
+        big_patch = P + q_big * (n_big - 1)
+        predict = {"value": mpix / pred_s, "unit": "Mpix/s", "seconds": pred_s,
+                   "mode": "shared windows: %d forward passes of %d^2 -> %d^2, each covering up to %dx%d "
+                           "of the %d sliding windows" % (n_win, S + q_big * (n_big - 1), big_patch, n_big,
+                                                          n_big, n_fwd),
+                   "executed_tflops": n_win * flops(big_patch) / pred_s / 1e12,
+                   "window_equivalents_per_s": n_fwd / pred_s,
+                   "window_loop": {"value": mpix / loop_s, "unit": "Mpix/s", "seconds": loop_s,
+                                   "patch_forwards_per_s": n_fwd / loop_s,
+                                   "tflops": n_fwd * flops(P) / loop_s / 1e12,
+                                   "mode": "one forward pass per sliding window (the reference's loop)"},
+                   "agreement": {"max_abs_diff": float(np.abs(masks - masks_loop).max()),
+                                 "pixels_equal_at_0.5": float(np.mean((masks > 0.5) == (masks_loop > 0.5)))},
+                   "config": "%d synthetic 604^2 image(s), stride 12, 6-way ensemble, work sharded over %d "
+                             "GPU(s), ConvolutionalModel.predict (host in / host out)"
+                             % (args.predict_images, world),
                    "mask_mean": float(masks.mean())}
 
     # ---- roofline of the dominant kernel: CUDA events around every tcgen05 launch (same steps,

@@ -10,6 +10,7 @@ patch list across ranks with a single final reduction of the per-rank partial ma
 """
 import argparse
 import glob
+import math
 import os
 import time
 from datetime import datetime
@@ -87,6 +88,10 @@ class Options(object):
             setattr(self, name, getattr(f, name))
         self.rotation_angles = None if not f.rotation_angles else \
             [int(i) for i in str(f.rotation_angles).split(",")]
+        # not a reference flag: predict() evaluates aligned sliding windows once (see
+        # shared_window_plan); RSU_SHARED_WINDOWS=0 runs every window as its own forward pass
+        self.shared_windows = os.environ.get("RSU_SHARED_WINDOWS", "1") != "0"
+        self.shared_window_max_input = int(os.environ.get("RSU_SHARED_WINDOW_MAX_INPUT", "1400"))
 
 
 # ------------------------------------------------------------------ distributed plumbing
@@ -114,6 +119,27 @@ class _Dist:
 def shard_range(n_items, rank, world):
     """Contiguous slice [k0, k1) of a work list owned by `rank` (prediction patches)."""
     return n_items * rank // world, n_items * (rank + 1) // world
+
+
+def shared_window_plan(side, stride, input_size, num_layers, max_input=1400):
+    """Sliding windows of a valid-padding U-Net whose origins differ by a multiple of the pooling
+    period 2^(L-1) compute identical features wherever they overlap.  Along one axis the `side`
+    patch positions k*stride fall into period/gcd(stride, period) alignment classes; the members
+    of a class lie q = lcm(stride, period) apart, so n of them are covered by ONE window of input
+    size input_size + q*(n-1) whose output holds the n patch outputs q apart.
+    Returns None when nothing can be shared, else (n, q, windows): windows = lists of the patch
+    positions (along the axis) that one window covers; its origin is stride * window[0]."""
+    period = 2 ** (num_layers - 1)
+    classes = period // math.gcd(stride, period)
+    q = stride * classes
+    n = min(-(-side // classes), 1 + max(0, (max_input - input_size) // q))
+    if n <= 1:
+        return None
+    windows = []
+    for a in range(min(classes, side)):
+        members = list(range(a, side, classes))
+        windows.extend(members[b:b + n] for b in range(0, len(members), n))
+    return n, q, windows
 
 
 def rank_batch_indices(indices, offset, rank, batch_size):
@@ -385,7 +411,35 @@ class ConvolutionalModel:
         side = (H - S) // opts.stride + 1
         num_patches = num_images * side * side
 
-        # this rank's contiguous slice of the patch list
+        plan = shared_window_plan(side, opts.stride, S, opts.num_layers, opts.shared_window_max_input) \
+            if getattr(opts, "shared_windows", False) else None
+        if plan is not None:
+            masks = self._predict_shared(x, num_images, side, plan)
+        else:
+            masks = self._predict_windows(x, num_images, side)
+
+        if opts.ensemble_prediction:
+            masks = images.invert_image_augmentation_ensemble_dev(masks[..., 0].contiguous())[..., None]
+
+        print("Prediction Done")
+        return masks.cpu().numpy().astype(np.float64)
+
+    def _overlap_counts(self, out_side, side):
+        """hit count of every mask pixel (analytic; used to normalise all-reduced partial sums)"""
+        P, stride = self._options.patch_size, self._options.stride
+        pos = np.arange(out_side)
+        lo = np.where(pos - P + 1 <= 0, 0, (pos - P + stride) // stride)
+        hi = np.minimum(pos // stride, side - 1)
+        cnt1 = (hi - lo + 1).astype(np.float32)
+        return torch.from_numpy(np.outer(cnt1, cnt1)).cuda()[None, :, :, None]
+
+    def _predict_windows(self, x, num_images, side):
+        """every sliding window is its own forward pass (the reference's loop, :296-315); ranks
+        take contiguous slices of the patch list"""
+        opts, net = self._options, self._net
+        world, rank = self._dist.world, self._dist.rank
+        S, P, B = self.input_size, opts.patch_size, opts.batch_size
+        num_patches = num_images * side * side
         k0, k1 = shard_range(num_patches, rank, world)
         preds = torch.empty(max(k1 - k0, 1), P, P, 1, dtype=torch.float32, device="cuda")
         if getattr(self, "_d_predict", None) is None:
@@ -401,24 +455,73 @@ class ConvolutionalModel:
 
         # construct masks: overlap average in gather form
         if world == 1:
-            masks = images.images_from_patches_dev(preds, num_images, side, opts.stride)
-        else:
-            part = images.images_from_patches_dev(preds, num_images, side, opts.stride, k0, k1 - k0,
-                                                  normalize=False)
-            self._dist.dist.all_reduce(part)  # the single exchange of a sharded prediction
-            Sout = part.shape[1]
-            pos = np.arange(Sout)
-            lo = np.where(pos - P + 1 <= 0, 0, (pos - P + opts.stride) // opts.stride)
-            hi = np.minimum(pos // opts.stride, side - 1)
-            cnt1 = (hi - lo + 1).astype(np.float32)
-            cnt2 = torch.from_numpy(np.outer(cnt1, cnt1)).cuda()
-            masks = part / cnt2[None, :, :, None]
+            return images.images_from_patches_dev(preds, num_images, side, opts.stride)
+        part = images.images_from_patches_dev(preds, num_images, side, opts.stride, k0, k1 - k0,
+                                              normalize=False)
+        self._dist.dist.all_reduce(part)  # the single exchange of a sharded prediction
+        return part / self._overlap_counts(part.shape[1], side)
 
-        if opts.ensemble_prediction:
-            masks = images.invert_image_augmentation_ensemble_dev(masks[..., 0].contiguous())[..., None]
+    def _shared_net(self, big_input, big_batch):
+        """forward-only engine for the enlarged windows, weights copied from the training engine"""
+        opts = self._options
+        nets = self.__dict__.setdefault("_shared_nets", {})
+        key = (big_input, big_batch)
+        if key not in nets:
+            nets.clear()  # one enlarged engine at a time (its activations are the big allocation)
+            nets[key] = unet.UNet(opts.num_layers, opts.root_size, opts.dilated_layers, big_batch,
+                                  big_input, seed=opts.seed, training=False)
+        big = nets[key]
+        big.params.copy_(self._net.params)
+        big.pack_weights()
+        return big
 
-        print("Prediction Done")
-        return masks.cpu().numpy().astype(np.float64)
+    def _predict_shared(self, x, num_images, side, plan):
+        """Aligned windows evaluated once (shared_window_plan): each forward pass covers n x n
+        windows of the reference's loop; their outputs are cut out of the enlarged output and
+        stored at their positions in the patch list, then overlap-averaged as usual.  Ranks take
+        contiguous slices of the enlarged-window list."""
+        opts = self._options
+        world, rank = self._dist.world, self._dist.rank
+        S, P, B, stride = self.input_size, opts.patch_size, opts.batch_size, opts.stride
+        n, q, wins = plan
+        big_in, big_out = S + q * (n - 1), P + q * (n - 1)
+        big_b = max(1, int(B * S * S / (big_in * big_in)))
+        big = self._shared_net(big_in, big_b)
+        assert big.P == big_out
+        # zero-extended copy of the padded images: every enlarged-window origin becomes a regular
+        # patch position of extract_patches (content beyond the image only reaches outputs that
+        # are never used)
+        H = x.shape[1]
+        side_z = max(w[0] for w in wins) + 1
+        Hz = max(H, stride * (side_z - 1) + big_in)
+        side_z = (Hz - big_in) // stride + 1
+        xz = torch.zeros(num_images, Hz, Hz, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+        xz[:, :H, :H].copy_(x)
+        jobs = [(img, wx, wy) for img in range(num_images) for wx in wins for wy in wins]
+        j0, j1 = shard_range(len(jobs), rank, world)
+        num_patches = num_images * side * side
+        alloc = torch.empty if world == 1 else torch.zeros
+        preds = alloc(num_patches, P, P, 1, dtype=torch.float32, device="cuda")
+        batch = torch.empty(big_b, big_in, big_in, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+        for j in range(j0, j1, big_b):
+            chunk = jobs[j:min(j + big_b, j1)]
+            src, dst = [], []
+            for i, (img, wx, wy) in enumerate(chunk):
+                images.extract_patches_dev(xz, big_in, stride, (img * side_z + wx[0]) * side_z + wy[0], 1,
+                                           out=batch[i:i + 1])
+                for mx, kx in enumerate(wx):
+                    for my, ky in enumerate(wy):
+                        src.append((i * n + mx) * n + my)
+                        dst.append((img * side + kx) * side + ky)
+            big.forward(batch, keep=1.0)
+            cut = images.extract_patches_dev(big.probs.view(big_b, big_out, big_out, 1), P, q)
+            preds.index_copy_(0, torch.tensor(dst, device="cuda"),
+                              cut.index_select(0, torch.tensor(src, device="cuda")))
+        if world == 1:
+            return images.images_from_patches_dev(preds, num_images, side, stride)
+        part = images.images_from_patches_dev(preds, num_images, side, stride, normalize=False)
+        self._dist.dist.all_reduce(part)  # the single exchange of a sharded prediction
+        return part / self._overlap_counts(part.shape[1], side)
 
     def predict_batchwise(self, imgs, pred_batch_size):
         masks = []

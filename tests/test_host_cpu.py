@@ -126,6 +126,29 @@ def test_host_visual_and_io_helpers(tmp_path):
     assert np.array_equal(gt[0], rgb[0, :, :, 0].astype(np.float32) / np.float32(255))
 
 
+def test_shared_window_plan():
+    """every sliding-window position is covered exactly once, members of a window are one
+    alignment period apart, and the enlarged input respects the cap"""
+    from road_segmentation_unet_b200 import tf_aerial_images as tfa
+    for side, stride, S, L, cap in ((19, 12, 764, 6, 1400), (54, 12, 764, 6, 1400), (5, 12, 124, 4, 1400),
+                                    (2, 12, 76, 3, 1400), (9, 110, 764, 6, 1400), (30, 16, 316, 5, 500),
+                                    (7, 32, 764, 6, 1400)):
+        plan = tfa.shared_window_plan(side, stride, S, L, cap)
+        period = 2 ** (L - 1)
+        if plan is None:
+            continue
+        n, q, wins = plan
+        assert q % period == 0 and q % stride == 0 and n >= 2
+        assert S + q * (n - 1) <= max(cap, S)
+        assert sorted(k for w in wins for k in w) == list(range(side))
+        for w in wins:
+            assert 1 <= len(w) <= n and all((b - a) * stride == q for a, b in zip(w, w[1:]))
+    assert tfa.shared_window_plan(19, 12, 764, 6)[0] == 3          # BASELINE configs[2]
+    assert tfa.shared_window_plan(19, 12, 764, 6, max_input=800) is None
+    assert tfa.shared_window_plan(1, 12, 764, 6) is None
+    assert tfa.shared_window_plan(7, 32, 764, 6)[1] == 32          # stride = period: one class
+
+
 def test_shard_helpers():
     from road_segmentation_unet_b200 import tf_aerial_images as tfa
     for n in (1, 7, 2166, 17328):

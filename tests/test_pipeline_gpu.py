@@ -216,3 +216,24 @@ def test_main_train_eval_submission(tmp_path):
     assert np.abs(masks - model.predict_batchwise(test_imgs, 2)).max() == 0.0
     lab = images.patch_labels(images.quantize_mask(masks, 0.25, 16), 16)
     assert [int(r.split(",")[1]) for r in rows[1:]] == lab.reshape(-1).tolist()
+
+
+@pytest.mark.parametrize("layers,patch,size,cap", [(3, 36, 72, 1400), (4, 36, 84, 1400), (4, 36, 84, 150)])
+def test_shared_windows_equal_window_loop(tmp_path, layers, patch, size, cap):
+    """predict() with aligned windows evaluated once (shared_window_plan) against the
+    reference's loop of one forward pass per window, same weights.  A window output inside an
+    enlarged window is the same dot products over the same receptive field; layer sizes differ,
+    so a layer may run in the other convolution kernel (another fp32 summation order) and a few
+    bf16 activations round the other way: observed <= 2e-5 on the probabilities."""
+    model, opts = make_model(tmp_path, num_layers=layers, patch_size=patch, ensemble_prediction=True)
+    opts.shared_window_max_input = cap
+    rs = np.random.RandomState(5)
+    imgs, _ = make_data(rs, 3, size)
+    assert model.input_size + 0 == {3: 76, 4: 124}[layers]
+    opts.shared_windows = True
+    shared = model.predict(imgs)
+    assert getattr(model, "_shared_nets", None), "the shared-window path did not run"
+    opts.shared_windows = False
+    loop = model.predict(imgs)
+    assert shared.shape == loop.shape == (3, size, size, 1)
+    assert np.abs(shared - loop).max() <= 2e-4 and np.abs(shared - loop).mean() <= 1e-5

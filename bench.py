@@ -310,13 +310,18 @@ def run_gpu(args):
         # are evaluated once inside an enlarged window (tf_aerial_images.shared_window_plan)
         masks, pred_s = timed_predict(True, imgs)  # warm-up allocates the enlarged engine
         n_big, q_big, wins = tfa.shared_window_plan(19, 12, S, CFG["num_layers"], opts.shared_window_max_input)
-        n_win = args.predict_images * 6 * len(wins) ** 2
-        big_patch = P + q_big * (n_big - 1)
+        sizes = {}
+        for wx in wins:
+            for wy in wins:
+                m = max(len(wx), len(wy))
+                sizes[m] = sizes.get(m, 0) + args.predict_images * 6
+        n_win = sum(sizes.values())
+        done_flops = sum(c * flops(P + q_big * (m - 1)) for m, c in sizes.items())
         predict = {"value": mpix / pred_s, "unit": "Mpix/s", "seconds": pred_s,
-                   "mode": "shared windows: %d forward passes of %d^2 -> %d^2, each covering up to %dx%d "
-                           "of the %d sliding windows" % (n_win, S + q_big * (n_big - 1), big_patch, n_big,
-                                                          n_big, n_fwd),
-                   "executed_tflops": n_win * flops(big_patch) / pred_s / 1e12,
+                   "mode": "shared windows: %s forward passes, each covering up to %dx%d of the %d sliding "
+                           "windows" % (" + ".join("%d of %d^2 -> %d^2" % (c, S + q_big * (m - 1), P + q_big * (m - 1))
+                                                   for m, c in sorted(sizes.items())), n_big, n_big, n_fwd),
+                   "executed_tflops": done_flops / pred_s / 1e12,
                    "window_equivalents_per_s": n_fwd / pred_s,
                    "window_loop": {"value": mpix / loop_s, "unit": "Mpix/s", "seconds": loop_s,
                                    "patch_forwards_per_s": n_fwd / loop_s,

@@ -462,12 +462,13 @@ class ConvolutionalModel:
         return part / self._overlap_counts(part.shape[1], side)
 
     def _shared_net(self, big_input, big_batch):
-        """forward-only engine for the enlarged windows, weights copied from the training engine"""
+        """forward-only engine for enlarged windows, weights copied from the training engine"""
         opts = self._options
         nets = self.__dict__.setdefault("_shared_nets", {})
         key = (big_input, big_batch)
         if key not in nets:
-            nets.clear()  # one enlarged engine at a time (its activations are the big allocation)
+            while len(nets) >= 2:  # their activations are the big allocations: keep two sizes
+                nets.pop(next(iter(nets)))
             nets[key] = unet.UNet(opts.num_layers, opts.root_size, opts.dilated_layers, big_batch,
                                   big_input, seed=opts.seed, training=False)
         big = nets[key]
@@ -476,47 +477,55 @@ class ConvolutionalModel:
         return big
 
     def _predict_shared(self, x, num_images, side, plan):
-        """Aligned windows evaluated once (shared_window_plan): each forward pass covers n x n
-        windows of the reference's loop; their outputs are cut out of the enlarged output and
-        stored at their positions in the patch list, then overlap-averaged as usual.  Ranks take
-        contiguous slices of the enlarged-window list."""
+        """Aligned windows evaluated once (shared_window_plan): each forward pass covers up to
+        n x n windows of the reference's loop; their outputs are cut out of the enlarged output
+        and stored at their positions in the patch list, then overlap-averaged as usual.  A job
+        (image, window along x, window along y) runs at the size of its longer window, so the
+        classes with fewer members use a smaller engine.  Ranks take contiguous slices of the
+        job list."""
         opts = self._options
         world, rank = self._dist.world, self._dist.rank
         S, P, B, stride = self.input_size, opts.patch_size, opts.batch_size, opts.stride
         n, q, wins = plan
-        big_in, big_out = S + q * (n - 1), P + q * (n - 1)
-        big_b = max(1, int(B * S * S / (big_in * big_in)))
-        big = self._shared_net(big_in, big_b)
-        assert big.P == big_out
         # zero-extended copy of the padded images: every enlarged-window origin becomes a regular
         # patch position of extract_patches (content beyond the image only reaches outputs that
         # are never used)
         H = x.shape[1]
-        side_z = max(w[0] for w in wins) + 1
-        Hz = max(H, stride * (side_z - 1) + big_in)
-        side_z = (Hz - big_in) // stride + 1
+        Hz = max(H, stride * max(w[0] for w in wins) + S + q * (n - 1))
         xz = torch.zeros(num_images, Hz, Hz, NUM_CHANNELS, dtype=torch.float32, device="cuda")
         xz[:, :H, :H].copy_(x)
         jobs = [(img, wx, wy) for img in range(num_images) for wx in wins for wy in wins]
         j0, j1 = shard_range(len(jobs), rank, world)
+        by_size = {}
+        for job in jobs[j0:j1]:
+            by_size.setdefault(max(len(job[1]), len(job[2])), []).append(job)
         num_patches = num_images * side * side
         alloc = torch.empty if world == 1 else torch.zeros
         preds = alloc(num_patches, P, P, 1, dtype=torch.float32, device="cuda")
-        batch = torch.empty(big_b, big_in, big_in, NUM_CHANNELS, dtype=torch.float32, device="cuda")
-        for j in range(j0, j1, big_b):
-            chunk = jobs[j:min(j + big_b, j1)]
-            src, dst = [], []
-            for i, (img, wx, wy) in enumerate(chunk):
-                images.extract_patches_dev(xz, big_in, stride, (img * side_z + wx[0]) * side_z + wy[0], 1,
-                                           out=batch[i:i + 1])
-                for mx, kx in enumerate(wx):
-                    for my, ky in enumerate(wy):
-                        src.append((i * n + mx) * n + my)
-                        dst.append((img * side + kx) * side + ky)
-            big.forward(batch, keep=1.0)
-            cut = images.extract_patches_dev(big.probs.view(big_b, big_out, big_out, 1), P, q)
-            preds.index_copy_(0, torch.tensor(dst, device="cuda"),
-                              cut.index_select(0, torch.tensor(src, device="cuda")))
+        for m, group in sorted(by_size.items()):
+            win_in, win_out = S + q * (m - 1), P + q * (m - 1)
+            if m == 1:
+                net, win_b = self._net, B
+            else:
+                win_b = max(1, int(B * S * S / (win_in * win_in)))
+                net = self._shared_net(win_in, win_b)
+            assert net.P == win_out and (Hz - win_in) % stride == 0
+            side_z = (Hz - win_in) // stride + 1
+            batch = torch.empty(win_b, win_in, win_in, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+            for j in range(0, len(group), win_b):
+                chunk = group[j:j + win_b]
+                src, dst = [], []
+                for i, (img, wx, wy) in enumerate(chunk):
+                    images.extract_patches_dev(xz, win_in, stride, (img * side_z + wx[0]) * side_z + wy[0],
+                                               1, out=batch[i:i + 1])
+                    for mx, kx in enumerate(wx):
+                        for my, ky in enumerate(wy):
+                            src.append((i * m + mx) * m + my)
+                            dst.append((img * side + kx) * side + ky)
+                net.forward(batch, keep=1.0)
+                cut = images.extract_patches_dev(net.probs.view(win_b, win_out, win_out, 1), P, q)
+                preds.index_copy_(0, torch.tensor(dst, device="cuda"),
+                                  cut.index_select(0, torch.tensor(src, device="cuda")))
         if world == 1:
             return images.images_from_patches_dev(preds, num_images, side, stride)
         part = images.images_from_patches_dev(preds, num_images, side, stride, normalize=False)

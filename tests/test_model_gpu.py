@@ -51,6 +51,7 @@ CASES = [
     (3, 64, False, 20, 2),
     (3, 64, True, 36, 2),
     (4, 64, True, 52, 1),
+    (4, 64, False, 388, 1),  # BASELINE.json configs[0] at full size: 476^2 -> 388^2, batch 1
 ]
 
 
@@ -126,6 +127,10 @@ def test_train_step_parity(case):
     # the device is as close to fp32 as the bf16-storage oracle is (both are independent samples
     # of the same flip noise, so compare the averages, not layer by layer)
     assert max(e32.values()) < 0.25, max(e32.values())
+    if P >= 128:
+        # at the full size of BASELINE.json configs[0] the flip noise averages out: every weight
+        # gradient of the free-running backward pass is within the 2e-2 gate of the fp32 oracle
+        assert max(e32.values()) < TOL, sorted(e32.items(), key=lambda kv: -kv[1])[:4]
     assert np.mean(list(e32.values())) < 2.0 * np.mean(list(floor.values())) + 1e-2
 
     # ---- momentum update (tf.train.MomentumOptimizer): same gradients -> same delta

@@ -52,6 +52,7 @@ CASES = [
     (3, 64, True, 36, 2),
     (4, 64, True, 52, 1),
     (4, 64, False, 388, 1),  # BASELINE.json configs[0] at full size: 476^2 -> 388^2, batch 1
+    (6, 64, True, 388, 1),   # the flagship architecture of configs[1..3] at full size, batch 1
 ]
 
 
@@ -127,9 +128,11 @@ def test_train_step_parity(case):
     # the device is as close to fp32 as the bf16-storage oracle is (both are independent samples
     # of the same flip noise, so compare the averages, not layer by layer)
     assert max(e32.values()) < 0.25, max(e32.values())
-    if P >= 128:
+    if P >= 128 and L <= 4:
         # at the full size of BASELINE.json configs[0] the flip noise averages out: every weight
         # gradient of the free-running backward pass is within the 2e-2 gate of the fp32 oracle
+        # (the 16^2-pixel bottom of the 6-level net at batch 1 stays flip-dominated, like the
+        # bf16-storage oracle itself: see the floor printed above)
         assert max(e32.values()) < TOL, sorted(e32.items(), key=lambda kv: -kv[1])[:4]
     assert np.mean(list(e32.values())) < 2.0 * np.mean(list(floor.values())) + 1e-2
 

@@ -507,7 +507,10 @@ class ConvolutionalModel:
             if m == 1:
                 net, win_b = self._net, B
             else:
+                # as many windows per pass as the training batch has pixels, evened out over the
+                # passes so that the last one is not mostly padding
                 win_b = max(1, int(B * S * S / (win_in * win_in)))
+                win_b = -(-len(group) // -(-len(group) // win_b))
                 net = self._shared_net(win_in, win_b)
             assert net.P == win_out and (Hz - win_in) % stride == 0
             side_z = (Hz - win_in) // stride + 1

@@ -384,47 +384,58 @@ __global__ void __launch_bounds__(256)
 
 // images.quantize_mask (images.py:256-266) and the patch labels behind save_submission_csv
 // (images.py:206-237: extract_patches(mask, p) -> labels_for_patches, images.py:88-99).
-// One block per p x p cell of one mask (cells at the right / bottom edge are clipped like the
-// reference's slices).  rule 0: label = mean(v >= pixel_thr) > vote_thr  (quantize_mask);
-// rule 1: label = mean(v) > vote_thr  (labels_for_patches).  Both means are taken in fp64, so the
-// vote rule is exact (a count divided by the cell area).  The label is written to every pixel
-// of the cell (quantized, optional) and / or to labels[n][x cell][y cell] -- x-outer, the order
-// of extract_patches and of the rows of submission.csv.
+// One block per row of p x p cells of one mask (cells at the right / bottom edge are clipped
+// like the reference's slices): a thread walks whole columns of the strip, so every warp reads
+// and writes contiguous row segments; column sums meet in shared memory and one thread per cell
+// adds its p columns in a fixed order.  rule 0: label = mean(v >= pixel_thr) > vote_thr
+// (quantize_mask); rule 1: label = mean(v) > vote_thr (labels_for_patches).  Both means are
+// taken in fp64, so the vote rule is exact (a count divided by the cell area).  The label is
+// written to every pixel of the cell (quantized, optional) and / or to
+// labels[n][x cell][y cell] -- x-outer, the order of extract_patches and of submission.csv.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    patch_vote_kernel(const T* __restrict__ masks, int S, int patch, int rule, double pixel_thr,
-                      double vote_thr, T* __restrict__ quantized, unsigned char* __restrict__ labels) {
-  __shared__ double part[8];
-  __shared__ int label_s;
-  const int cx = blockIdx.x, cy = blockIdx.y, n = blockIdx.z;
-  const int x0 = cx * patch, y0 = cy * patch;
-  const int w = min(patch, S - x0), h = min(patch, S - y0);
-  const T* __restrict__ src = masks + (1LL * n * S + y0) * S + x0;
-  double acc = 0.0;
-  for (int e = threadIdx.x; e < w * h; e += blockDim.x) {
-    const int yy = e / w, xx = e - yy * w;
-    const double v = static_cast<double>(src[1LL * yy * S + xx]);
-    acc += rule == 0 ? (v >= pixel_thr ? 1.0 : 0.0) : v;
-  }
+    patch_vote_kernel(const T* __restrict__ masks, int S, int patch, int cells, int rule,
+                      double pixel_thr, double vote_thr, T* __restrict__ quantized,
+                      unsigned char* __restrict__ labels) {
+  extern __shared__ double col_sum[];                                     // [S] then labels [cells]
+  unsigned char* label_s = reinterpret_cast<unsigned char*>(col_sum + S);
+  const int cy = blockIdx.x, n = blockIdx.y;
+  const int y0 = cy * patch, h = min(patch, S - y0);
+  const T* __restrict__ src = masks + (1LL * n * S + y0) * S;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) {
+    double acc = 0.0;
+    int yy = 0;
+    for (; yy + 4 <= h; yy += 4) {  // four rows in flight per thread
+      T v[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double sum = 0.0;
-    for (int q = 0; q < static_cast<int>(blockDim.x >> 5); ++q) sum += part[q];
-    const int label = sum / static_cast<double>(w * h) > vote_thr ? 1 : 0;
-    label_s = label;
-    if (labels != nullptr) labels[(1LL * n * gridDim.x + cx) * gridDim.y + cy] = static_cast<unsigned char>(label);
+      for (int u = 0; u < 4; ++u) v[u] = src[1LL * (yy + u) * S + x];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double d = static_cast<double>(v[u]);
+        acc += rule == 0 ? (d >= pixel_thr ? 1.0 : 0.0) : d;
+      }
+    }
+    for (; yy < h; ++yy) {
+      const double d = static_cast<double>(src[1LL * yy * S + x]);
+      acc += rule == 0 ? (d >= pixel_thr ? 1.0 : 0.0) : d;
+    }
+    col_sum[x] = acc;
   }
   __syncthreads();
-  if (quantized != nullptr) {
-    const T lv = static_cast<T>(label_s);
-    T* __restrict__ dst = quantized + (1LL * n * S + y0) * S + x0;
-    for (int e = threadIdx.x; e < w * h; e += blockDim.x) {
-      const int yy = e / w, xx = e - yy * w;
-      dst[1LL * yy * S + xx] = lv;
-    }
+  for (int cx = threadIdx.x; cx < cells; cx += blockDim.x) {
+    const int x0 = cx * patch, w = min(patch, S - x0);
+    double sum = 0.0;
+    for (int xx = 0; xx < w; ++xx) sum += col_sum[x0 + xx];
+    const unsigned char label = sum / static_cast<double>(w * h) > vote_thr ? 1 : 0;
+    label_s[cx] = label;
+    if (labels != nullptr) labels[(1LL * n * cells + cx) * cells + cy] = label;
+  }
+  if (quantized == nullptr) return;
+  __syncthreads();
+  T* __restrict__ dst = quantized + (1LL * n * S + y0) * S;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) {
+    const T lv = static_cast<T>(label_s[x / patch]);
+    for (int yy = 0; yy < h; ++yy) dst[1LL * yy * S + x] = lv;
   }
 }
 
@@ -671,17 +682,19 @@ int rsu_patch_vote(const void* masks, int elem_bytes, int N, int S, int patch, i
     return set_error(RSU_EINVAL, "patch_vote: shape / rule");
   if (elem_bytes != 4 && elem_bytes != 8) return set_error(RSU_EINVAL, "patch_vote: fp32 or fp64 masks");
   const int g = (S + patch - 1) / patch;
-  if (N > 65535 || g > 65535) return set_error(RSU_EINVAL, "patch_vote: grid too large");
-  const dim3 grid(g, g, N);
+  if (N > 65535) return set_error(RSU_EINVAL, "patch_vote: N > 65535");
+  const size_t smem = sizeof(double) * S + ((g + 7) / 8) * 8;
+  if (smem > 48 * 1024) return set_error(RSU_EINVAL, "patch_vote: mask side %d too large", S);
+  const dim3 grid(g, N);
   const cudaStream_t st = (cudaStream_t)stream;
   if (elem_bytes == 4)
-    patch_vote_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(masks), S, patch, rule,
-                                                   pixel_threshold, vote_threshold,
-                                                   static_cast<float*>(quantized), labels);
+    patch_vote_kernel<float><<<grid, 256, smem, st>>>(static_cast<const float*>(masks), S, patch, g, rule,
+                                                      pixel_threshold, vote_threshold,
+                                                      static_cast<float*>(quantized), labels);
   else
-    patch_vote_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(masks), S, patch, rule,
-                                                    pixel_threshold, vote_threshold,
-                                                    static_cast<double*>(quantized), labels);
+    patch_vote_kernel<double><<<grid, 256, smem, st>>>(static_cast<const double*>(masks), S, patch, g, rule,
+                                                       pixel_threshold, vote_threshold,
+                                                       static_cast<double*>(quantized), labels);
   return check_launch("patch_vote");
 }
 

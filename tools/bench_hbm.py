@@ -94,6 +94,10 @@ def run(n_img=24):
     ms = timed(lambda: images.rotate_crop_dev(pad, 30, 776))
     add("rotate_nn_crop", 8 * (832 ** 2 + 776 ** 2) * 3 * 4, ms, "8x832^2x3 -> 776^2, 30 deg")
 
+    probs = torch.rand(96, 608, 608, device="cuda", generator=g)
+    ms = timed(lambda: images.patch_vote_dev(probs, 16, images.RULE_VOTE, 0.25, quantized=True, labels=True))
+    add("patch_vote (quantize_mask)", 2 * probs.numel() * 4, ms, "96x608^2 fp32 -> quantised masks + 38x38 labels")
+
     masks = torch.rand(6 * 16, 604, 604, device="cuda", generator=g)
     ms = timed(lambda: images.invert_image_augmentation_ensemble_dev(masks))
     add("ensemble_invert", masks.numel() * 4 + 16 * 604 * 604 * 4, ms, "96x604^2 -> 16x604^2")

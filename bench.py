@@ -17,6 +17,8 @@ Inputs per step (19 GB of activations) are far larger than the 126 MB L2, so no 
 step of the same model.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -459,10 +461,27 @@ def main():
     ap.add_argument("--predict-images", type=int, default=1, help="604^2 images in the prediction leg")
     ap.add_argument("--dump-layers", default="", help="write the per-layer tcgen05 kernel timing table here")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    # stdout carries exactly ONE line, the JSON record: everything else that libraries write to
+    # file descriptor 1 (NCCL prints its version banner there) is routed to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        lines = [ln for ln in buf.getvalue().splitlines() if ln.strip()]
+        for ln in lines[:-1]:
+            print(ln, file=sys.stderr)
+        if lines:
+            print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":

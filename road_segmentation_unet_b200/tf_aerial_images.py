@@ -92,6 +92,8 @@ class Options(object):
         # shared_window_plan); RSU_SHARED_WINDOWS=0 runs every window as its own forward pass
         self.shared_windows = os.environ.get("RSU_SHARED_WINDOWS", "1") != "0"
         self.shared_window_max_input = int(os.environ.get("RSU_SHARED_WINDOW_MAX_INPUT", "1400"))
+        # "auto": training steps of batch <= 8 are replayed from CUDA graphs; "0" / "1" force it
+        self.cuda_graphs = os.environ.get("RSU_CUDA_GRAPHS", "auto")
 
 
 # ------------------------------------------------------------------ distributed plumbing
@@ -286,6 +288,46 @@ class ConvolutionalModel:
         self._staged[id(patches_batch)] = (patches_batch, labels_batch, slot, ev)
         return True
 
+    def _step_graphs(self, lr):
+        """CUDA graphs of one training step, or None when the step runs eagerly.
+
+        A step is a fixed sequence of ~140 launches over preallocated buffers; at small batch
+        sizes (the README recipe trains at batch 1) issuing them from Python takes longer than
+        the GPU needs to run them, so the sequence is captured once -- forward pass in one graph,
+        backward pass + momentum update + weight repack in a second (the fetch of loss and
+        probabilities starts between the two) -- and replayed.  The learning rate is a kernel
+        argument: the graphs are re-captured when exponential_decay changes it (every 1,000
+        steps).  Eager: the first step of a process (one-time kernel attribute set-up), dropout
+        < 1 (per-step seeds), data-parallel runs (NCCL buckets on a side stream), profiling."""
+        opts = self._options
+        mode = getattr(opts, "cuda_graphs", "auto")
+        want = mode == "1" or (mode == "auto" and opts.batch_size <= 8)
+        from . import ops as _ops
+        if (not want or opts.dropout != 1.0 or self._dist.active or _ops._PROFILE is not None
+                or getattr(self, "_eager_steps", 0) < 1):
+            return None
+        cached = getattr(self, "_graphs", None)
+        if cached is not None and cached[0] == lr:
+            return cached
+        net = self._net
+        B, S, P = opts.batch_size, self.input_size, opts.patch_size
+        if cached is None:
+            gx = torch.empty(B, S, S, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+            gy = torch.empty(B, P, P, dtype=torch.uint8, device="cuda")
+        else:
+            gx, gy = cached[1], cached[2]
+        self._graphs = None
+        g_fwd, g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fwd):
+            net.grads.zero_()
+            net.forward(gx, gy, keep=1.0)
+        with torch.cuda.graph(g_bwd, pool=g_fwd.pool()):
+            net.backward()
+            net.apply_gradients(opts.lr, opts.momentum, 1.0)
+        net.global_step -= 1  # capture ran the host side of apply_gradients, not its kernels
+        self._graphs = (lr, gx, gy, g_fwd, g_bwd)
+        return self._graphs
+
     def train_batch(self, patches_batch, labels_batch):
         """patches_batch [B,S,S,3], labels_batch [B,P,P] (host arrays).  Returns (loss, probs)."""
         opts = self._options
@@ -306,8 +348,14 @@ class ConvolutionalModel:
         if opts.image_augmentation:
             x, y = self.stochastic_images_augmentation(x, y)
         lr = net.learning_rate(opts.lr)
-        net.grads.zero_()
-        net.forward(x, y, keep=opts.dropout)
+        graphs = self._step_graphs(lr)
+        if graphs is None:
+            net.grads.zero_()
+            net.forward(x, y, keep=opts.dropout)
+        else:  # replay the captured forward pass on the step's inputs
+            graphs[1].copy_(x)
+            graphs[2].copy_(y)
+            graphs[3].replay()
         # loss and probabilities are final once the forward pass is: their device->host copies run
         # on the copy stream underneath the backward pass
         fwd_done = torch.cuda.Event()
@@ -318,14 +366,20 @@ class ConvolutionalModel:
             self._h_loss.copy_(net.loss, non_blocking=True)
             fetched = torch.cuda.Event()
             fetched.record(self._copy_stream)
-        net.backward()
+        if graphs is None:
+            net.backward()
+        else:  # backward pass + momentum update + weight repack, captured together
+            graphs[4].replay()
+            net.global_step += 1
         # (the inputs are read by the forward pass and by the first-layer weight gradient at the
         # very end of the backward pass: only now may a prefetch overwrite this slot)
         free = torch.cuda.Event()
         free.record(cur)
         self._slot_free[self._slot] = free
-        scale = self._reducer.finish() if self._reducer is not None else 1.0
-        net.apply_gradients(opts.lr, opts.momentum, scale)
+        if graphs is None:
+            scale = self._reducer.finish() if self._reducer is not None else 1.0
+            net.apply_gradients(opts.lr, opts.momentum, scale)
+            self._eager_steps = getattr(self, "_eager_steps", 0) + 1
         # the step's fetches (loss, probabilities) are what the caller waits for; the update that
         # follows them on the stream is ordered before everything the next call enqueues
         fetched.synchronize()

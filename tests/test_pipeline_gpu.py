@@ -237,3 +237,32 @@ def test_shared_windows_equal_window_loop(tmp_path, layers, patch, size, cap):
     loop = model.predict(imgs)
     assert shared.shape == loop.shape == (3, size, size, 1)
     assert np.abs(shared - loop).max() <= 2e-4 and np.abs(shared - loop).mean() <= 1e-5
+
+
+def test_cuda_graph_steps_match_eager(tmp_path):
+    """train_batch replayed from CUDA graphs (small batches) against the same steps launched
+    eagerly: same losses, same weights (up to the summation order of the fp32 atomics in the
+    weight gradients), same step counter -- across a change of the staircase learning rate,
+    which re-captures the graphs."""
+    eager, o_e = make_model(tmp_path / "e")
+    graph, o_g = make_model(tmp_path / "g")
+    o_e.cuda_graphs, o_g.cuda_graphs = "0", "1"
+    B, S, P = o_e.batch_size, eager.input_size, o_e.patch_size
+    rs = np.random.RandomState(21)
+    for m in (eager, graph):
+        m.net.global_step = 997
+    lrs = []
+    for step in range(6):
+        x = rs.rand(B, S, S, 3).astype(np.float32)
+        lab = (rs.rand(B, P, P) > 0.7).astype(np.float32)
+        le, pe = eager.train_batch(x, lab)
+        lg, pg = graph.train_batch(x, lab)
+        assert abs(le - lg) <= 5e-3 * abs(le), (step, le, lg)
+        assert np.abs(pe - pg).max() <= 2e-2
+        lrs.append(graph.scalars[-1][2])
+    assert graph._graphs is not None and getattr(eager, "_graphs", None) is None
+    assert eager.global_step == graph.global_step == 1003
+    assert lrs[:3] == [o_g.lr] * 3 and all(abs(v - o_g.lr * 0.95) < 1e-12 for v in lrs[3:])
+    for name in eager.net.live_variables():
+        a, b = eager.net.var(name).cpu().numpy(), graph.net.var(name).cpu().numpy()
+        assert np.linalg.norm(a - b) <= 1e-3 * np.linalg.norm(a) + 1e-5, name

@@ -144,6 +144,18 @@ def shared_window_plan(side, stride, input_size, num_layers, max_input=1400):
     return n, q, windows
 
 
+def shared_window_jobs(num_images, windows, rank=0, world=1):
+    """The enlarged-window jobs (image, window along x, window along y) of one rank -- a contiguous
+    slice of the image-major job list -- grouped by the number of window positions per side the
+    job needs (the longer of its two windows), i.e. by the engine size that runs it."""
+    jobs = [(img, wx, wy) for img in range(num_images) for wx in windows for wy in windows]
+    j0, j1 = shard_range(len(jobs), rank, world)
+    by_size = {}
+    for job in jobs[j0:j1]:
+        by_size.setdefault(max(len(job[1]), len(job[2])), []).append(job)
+    return by_size
+
+
 def rank_batch_indices(indices, offset, rank, batch_size):
     """The slice of the (identically shuffled) epoch permutation that `rank` trains on at the
     global step starting at `offset`: ranks take consecutive batch_size-sized pieces."""
@@ -548,11 +560,7 @@ class ConvolutionalModel:
         Hz = max(H, stride * max(w[0] for w in wins) + S + q * (n - 1))
         xz = torch.zeros(num_images, Hz, Hz, NUM_CHANNELS, dtype=torch.float32, device="cuda")
         xz[:, :H, :H].copy_(x)
-        jobs = [(img, wx, wy) for img in range(num_images) for wx in wins for wy in wins]
-        j0, j1 = shard_range(len(jobs), rank, world)
-        by_size = {}
-        for job in jobs[j0:j1]:
-            by_size.setdefault(max(len(job[1]), len(job[2])), []).append(job)
+        by_size = shared_window_jobs(num_images, wins, rank, world)
         num_patches = num_images * side * side
         alloc = torch.empty if world == 1 else torch.zeros
         preds = alloc(num_patches, P, P, 1, dtype=torch.float32, device="cuda")

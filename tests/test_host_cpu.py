@@ -147,6 +147,19 @@ def test_shared_window_plan():
     assert tfa.shared_window_plan(19, 12, 764, 6, max_input=800) is None
     assert tfa.shared_window_plan(1, 12, 764, 6) is None
     assert tfa.shared_window_plan(7, 32, 764, 6)[1] == 32          # stride = period: one class
+    # the jobs of all ranks together evaluate every (image, x position, y position) exactly once,
+    # and a job runs at the size of its longer window
+    n, q, wins = tfa.shared_window_plan(19, 12, 764, 6)
+    for world in (1, 2, 3, 8):
+        seen = []
+        for rank in range(world):
+            for m, group in tfa.shared_window_jobs(6, wins, rank, world).items():
+                for img, wx, wy in group:
+                    assert max(len(wx), len(wy)) == m <= n
+                    seen.extend((img, kx, ky) for kx in wx for ky in wy)
+        assert sorted(seen) == [(i, kx, ky) for i in range(6) for kx in range(19) for ky in range(19)]
+    sizes = {m: len(g) for m, g in tfa.shared_window_jobs(6, wins).items()}
+    assert sizes == {2: 150, 3: 234}                               # bench.py's predict.mode line
 
 
 def test_shard_helpers():

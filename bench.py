@@ -207,7 +207,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def device_step():
-        net.grads.zero_()
+        net.zero_grads()
         net.forward(x, lab, keep=1.0)
         net.backward()
         scale = model._reducer.finish() if model._reducer is not None else 1.0

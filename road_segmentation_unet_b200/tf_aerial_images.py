@@ -331,7 +331,7 @@ class ConvolutionalModel:
         self._graphs = None
         g_fwd, g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_fwd):
-            net.grads.zero_()
+            net.zero_grads()
             net.forward(gx, gy, keep=1.0)
         with torch.cuda.graph(g_bwd, pool=g_fwd.pool()):
             net.backward()
@@ -362,7 +362,7 @@ class ConvolutionalModel:
         lr = net.learning_rate(opts.lr)
         graphs = self._step_graphs(lr)
         if graphs is None:
-            net.grads.zero_()
+            net.zero_grads()
             net.forward(x, y, keep=opts.dropout)
         else:  # replay the captured forward pass on the step's inputs
             graphs[1].copy_(x)

@@ -595,15 +595,34 @@ class UNet:
         """tf.train.exponential_decay(lr, global_step, 1000, 0.95, staircase=True)."""
         return lr0 * 0.95 ** (self.global_step // 1000)
 
+    def live_ranges(self):
+        """Slices of the flat parameter vector that ever receive a gradient: everything but the
+        dead dilated pair of the deepest level (unet.py:57-59), whose gradient and momentum stay
+        zero -- TensorFlow creates no ApplyMomentum op for it either."""
+        if getattr(self, "_live_ranges", None) is None:
+            if self.dilated:
+                d0 = self.offsets["conv_dilut_%d/atrous_conv1/kernel" % (self.L - 1)]
+                d1 = self.offsets["conv_%d/conv1/kernel" % (self.L - 1)]
+                self._live_ranges = [(a, b) for a, b in ((0, d0), (d1, self.n_flat)) if b > a]
+            else:
+                self._live_ranges = [(0, self.n_flat)]
+        return self._live_ranges
+
+    def zero_grads(self):
+        for a, b in self.live_ranges():
+            self.grads[a:b].zero_()
+
     def apply_gradients(self, lr0, momentum, grad_scale=1.0):
-        ops.momentum_sgd(self.params, self.momentum, self.grads, self.learning_rate(lr0), momentum,
-                         grad_scale)
+        lr = self.learning_rate(lr0)
+        for a, b in self.live_ranges():
+            ops.momentum_sgd(self.params[a:b], self.momentum[a:b], self.grads[a:b], lr, momentum,
+                             grad_scale)
         self.global_step += 1
         self.pack_weights()
 
     def train_step(self, images, labels, lr0=0.01, momentum=0.9, keep=1.0, allreduce=None):
         """forward + backward + momentum update; returns the device scalar loss tensor."""
-        self.grads.zero_()
+        self.zero_grads()
         self.forward(images, labels, keep)
         self.backward()
         scale = 1.0

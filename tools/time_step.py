@@ -26,7 +26,7 @@ def main():
     for it in range(a.steps):
         ops._lib.load().rsu_reset_launch_count()
         ev[0].record()
-        net.grads.zero_()
+        net.zero_grads()
         net.forward(x, lab)
         ev[1].record()
         net.backward()

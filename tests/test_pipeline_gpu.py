@@ -266,3 +266,30 @@ def test_cuda_graph_steps_match_eager(tmp_path):
     for name in eager.net.live_variables():
         a, b = eager.net.var(name).cpu().numpy(), graph.net.var(name).cpu().numpy()
         assert np.linalg.norm(a - b) <= 1e-3 * np.linalg.norm(a) + 1e-5, name
+
+
+def test_stochastic_images_augmentation(tmp_path):
+    """tf_aerial_images.py:173-210: per sample three fair coins each applying flip_up_down (:188),
+    then rot90 by floor(4U) -- the same dihedral element on the image and on its mask, bit-exact
+    per element, all 8 elements reachable, roughly uniform."""
+    model, opts = make_model(tmp_path, batch_size=8)
+    S, P = model.input_size, opts.patch_size
+    rs = np.random.RandomState(13)
+    x = rs.rand(8, S, S, 3).astype(np.float32)
+    m = (rs.rand(8, P, P) > 0.5).astype(np.uint8)
+    xd, md = torch.tensor(x).cuda(), torch.tensor(m).cuda()
+    seen = {}
+    for _ in range(40):
+        state = model._aug_rng.get_state()
+        xa, ma = model.stochastic_images_augmentation(xd, md)
+        replay = np.random.RandomState()
+        replay.set_state(state)  # the draws the call consumed: 3 x B coins, then B rotations
+        coins = replay.random_sample((3, 8)) > 0.5
+        flip = coins[0] ^ coins[1] ^ coins[2]
+        k = np.floor(replay.random_sample(8) * 4).astype(int)
+        xa, ma = xa.cpu().numpy(), ma.cpu().numpy()
+        for b in range(8):
+            assert np.array_equal(xa[b], O.d4_apply(x[b], flip[b], k[b]))
+            assert np.array_equal(ma[b], O.d4_apply(m[b], flip[b], k[b]))
+            seen[(bool(flip[b]), int(k[b]))] = seen.get((bool(flip[b]), int(k[b])), 0) + 1
+    assert len(seen) == 8 and min(seen.values()) >= 15, seen  # 320 draws, 40 expected per element

@@ -71,7 +71,9 @@ typedef struct {
   const void* mask; /* bf16, same indexing as out with its own strides: keep where mask > 0 */
   long long mask_sn, mask_sy, mask_sx;
   int accumulate; /* out += result */
-  int algo;       /* 0 = choose, 1 = one TMA box per tap, 2 = halo tile shared by all taps */
+  int algo;       /* 0 = choose, 1 = one TMA box per tap, 2 = halo tile shared by all taps,
+                     3 = algorithm 1 on CTA pairs (tcgen05.mma.cta_group::2, N tile 128 / 256;
+                     experimental, never chosen by 0) */
   /* mask_nc > 0: the mask tensor has mask_nc channels and covers output channels
    * [mask_c0, mask_c0 + mask_nc) only (the ReluGrad of one member of a concat gradient,
    * unet.py:70-85); both multiples of the N tile (64 / 128 / 256, the largest dividing Ntot). */

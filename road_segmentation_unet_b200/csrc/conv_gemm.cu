@@ -277,6 +277,8 @@ static int conv_smem_bytes(int BN, int num_k, int* stages_out) {
 }
 
 int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forced);  // conv_halo.cu
+int launch_conv_gemm2(ConvGemmParams& p, const void* weights, int ktot, int ntot,
+                      cudaStream_t stream);  // conv_gemm2.cu
 
 }  // namespace rsu
 
@@ -373,6 +375,7 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
     return set_error(RSU_EINVAL, "mask channel range [%d, +%d) not a multiple of the N tile %d", d->mask_c0,
                      d->mask_nc, p.BN);
   p.accumulate = d->accumulate;
+  if (d->algo == 3) return launch_conv_gemm2(p, d->weights, ktot, d->Ntot, stream);
 
   int stages;
   const int smem = conv_smem_bytes(p.BN, ktot / kBlockK, &stages);

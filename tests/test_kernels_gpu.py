@@ -552,3 +552,43 @@ def test_conv3x3_wgrad_halo(ops, case):
     assert done
     assert rel_err(out.cpu().numpy(), ref) < 2e-3
     assert rel_err(db.cpu().numpy(), dz.sum(axis=(0, 1, 2))) < 2e-3
+
+
+@pytest.mark.parametrize("case", [
+    # (N, H, Cin, Cout, dilation)
+    (2, 37, 128, 256, 1),   # BN = 256, ragged edges, even tile count
+    (1, 30, 64, 512, 2),    # two N tiles, dilation 2, odd tile count (idle half of the last pair)
+    (3, 20, 256, 128, 1),   # BN = 128: 64 weight rows per CTA
+])
+def test_conv3x3_cta_pair(ops, case):
+    """conv_gemm2_kernel (tcgen05.mma.cta_group::2, algo 3) against the single-CTA kernel: the
+    same dot products in the same K order, so the outputs are identical; forward (bias + ReLU)
+    and data gradient (ReLU-grad mask, accumulate)."""
+    n, h, cin, cout, d = case
+    rs = np.random.RandomState(31)
+    x = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    w = bf((rs.randn(3, 3, cin, cout) / np.sqrt(9 * cin)).astype(np.float32))
+    b = rs.randn(cout).astype(np.float32)
+    ho = h - 2 * d
+    outs = []
+    for algo in (ops.ALGO_PER_TAP, ops.ALGO_PER_TAP_PAIR):
+        out = torch.full((n, ho, ho, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+        ops.conv3x3_fwd([(dev(x), 0, 0)], pack_fwd(ops, w), dev(b, torch.float32), out, dilation=d, algo=algo)
+        torch.cuda.synchronize()
+        outs.append(out.float().cpu().numpy())
+    ref = torch.relu(O.conv2d_valid(torch.tensor(x), torch.tensor(w), torch.tensor(b), d)).numpy()
+    assert rel_err(outs[1], ref) < 6e-3
+    assert np.array_equal(outs[0], outs[1])
+    # data gradient into a window that already holds a value (accumulate), masked
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    mask_src = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    base = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    grads = []
+    if cin % 128 == 0:
+        for algo in (ops.ALGO_PER_TAP, ops.ALGO_PER_TAP_PAIR):
+            out = dev(base)
+            ops.conv3x3_dgrad(dev(dz), pack_dgrad(ops, w), out, dilation=d, mask=dev(mask_src),
+                              accumulate=True, algo=algo)
+            torch.cuda.synchronize()
+            grads.append(out.float().cpu().numpy())
+        assert np.array_equal(grads[0], grads[1])

@@ -16,6 +16,8 @@
 //
 // Reference ops replaced: tf.layers.conv2d (+dilation_rate) fwd and Conv2DBackpropInput,
 // tf.layers.conv2d_transpose fwd/bwd, crop + concat (src/unet.py:34-45, 67-91).
+#include <stdlib.h>
+
 #include "gemm_params.h"
 #include "host_common.h"
 #include "ptx.cuh"
@@ -375,7 +377,15 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
     return set_error(RSU_EINVAL, "mask channel range [%d, +%d) not a multiple of the N tile %d", d->mask_c0,
                      d->mask_nc, p.BN);
   p.accumulate = d->accumulate;
-  if (d->algo == 3) return launch_conv_gemm2(p, d->weights, ktot, d->Ntot, stream);
+  // CTA pairs (conv_gemm2.cu) wherever this kernel would run with the 256-wide N tile: 3-13 %
+  // faster on every such layer of the flagship network (tools/bench_pair.py,
+  // profiles/r1_pair_ab.txt); at N = 128 the single-CTA kernels win.  RSU_CONV_PAIR=0 disables.
+  static const bool pair_auto = [] {
+    const char* e = getenv("RSU_CONV_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  if (d->algo == 3 || (d->algo == 0 && pair_auto && p.BN == 256))
+    return launch_conv_gemm2(p, d->weights, ktot, d->Ntot, stream);
 
   int stages;
   const int smem = conv_smem_bytes(p.BN, ktot / kBlockK, &stages);

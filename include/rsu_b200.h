@@ -105,7 +105,9 @@ typedef struct {
                        (BiasAddGrad fused into the halo-tile kernel; NULL = not wanted).  On
                        return *bias_done tells whether the kernel produced it. */
   int* bias_done_host;
-  int algo; /* 0 = choose, 1 = one TMA box per tap pair, 2 = halo tile shared by all taps */
+  int algo; /* 0 = choose, 1 = one TMA box per tap pair, 2 = halo tile shared by all taps,
+               3 = algorithm 1 on CTA pairs (EXPERIMENTAL, not validated on hardware; no bias
+               gradient; never chosen by 0) */
 } rsu_wgrad_desc;
 int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream);
 

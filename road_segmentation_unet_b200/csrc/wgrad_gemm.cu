@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 }
 
 int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_done);  // wgrad_halo.cu
+int launch_wgrad_gemm2(WgradParams& p, cudaStream_t stream);                           // wgrad_gemm2.cu
 
 // pixels per K step of the per-tap kernel (RSU_WGRAD_TILE = 32 | 64 | 128 overrides, for A/B runs)
 static int wgrad_tile_pixels() {
@@ -382,6 +383,10 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   p.n_tiles_n = cout / p.BN;
   p.out = d->out;
   p.ldo = d->ldo;
+
+  // experimental CTA-pair kernel (not validated on hardware yet: explicit request only); it has no
+  // ones atom, so the bias gradient is left to the caller (*bias_done_host stays 0)
+  if (d->algo == 3) return launch_wgrad_gemm2(p, stream);
 
   const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
   const int mn_units = p.n_tiles_m * p.n_tiles_n;

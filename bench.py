@@ -165,8 +165,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "U-Net L=6 root=64 dilated, 764^2->388^2 patches, fwd+bwd+momentum SGD "
-                               "(BASELINE.json configs[1]); CPU arm runs batch 1 per step"},
+        "config": {"workload": "U-Net num_layers=6 root_size=64 --dilated_layers, batch 32/GPU of "
+                               "764^2->388^2 patches, momentum SGD lr 0.01 mu 0.9, dropout 1.0 "
+                               "(BASELINE.json configs[1])",
+                   "sample": "the CPU arm times batch 1 of that step (patches/s does not depend on the batch "
+                             "size on the CPU)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d steps of batch 1 of the same model, fp32 torch-CPU oracle" % steps},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

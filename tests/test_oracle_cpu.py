@@ -166,3 +166,31 @@ def test_learning_rate_staircase():
     assert UO.learning_rate(0.01, 999) == 0.01
     assert abs(UO.learning_rate(0.01, 1000) - 0.0095) < 1e-12
     assert abs(UO.learning_rate(0.01, 2500) - 0.01 * 0.95 ** 2) < 1e-12
+
+
+@pytest.mark.parametrize("dilated", [False, True])
+def test_shared_window_principle(dilated):
+    """The property behind ConvolutionalModel._predict_shared, checked on the CPU oracle in fp64:
+    sliding windows whose origins differ by a multiple of the pooling period 2^(L-1) are crops
+    of ONE forward pass over the enlarged window (valid convolutions, aligned pooling, size-
+    independent centre-crop offsets) -- and a shift that is not a multiple of the period is not."""
+    L, root, P = 3, 8, 20
+    S = UO.input_size_needed(P, L)            # 60
+    period = 2 ** (L - 1)                     # 4
+    q = 12                                    # lcm(stride 12, period 4): windows 12 pixels apart
+    params = {k: torch.tensor(v, dtype=torch.float64) for k, v in UO.init_params(L, root, dilated, 2017).items()}
+    rs = np.random.RandomState(1)
+    img = torch.tensor(rs.rand(1, S + 2 * q, S + 2 * q, 3))
+    with torch.no_grad():
+        big = UO.forward(img, params, L, root, dilated)          # enlarged window: 3 x 3 positions
+        assert big.shape[1] == P + 2 * q
+        for jy in range(3):
+            for jx in range(3):
+                win = img[:, jy * q:jy * q + S, jx * q:jx * q + S]
+                one = UO.forward(win, params, L, root, dilated)
+                cut = big[:, jy * q:jy * q + P, jx * q:jx * q + P]
+                assert float((one - cut).abs().max()) < 1e-12, (jy, jx)
+        # a window shifted by half a period sees other pooling windows: not a crop of `big`
+        off = period // 2
+        one = UO.forward(img[:, off:off + S, :S], params, L, root, dilated)
+        assert float((one - big[:, off:off + P, :P]).abs().max()) > 1e-6

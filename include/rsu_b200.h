@@ -38,6 +38,11 @@ int rsu_version(void);
 long long rsu_launch_count(void);
 void rsu_reset_launch_count(void);
 
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum
+ * TensorFlow's checkpoint bundle stores per tensor and per index block (tf.train.Saver,
+ * tf_aerial_images.py:171, :343-379 -> tensorflow/core/util/tensor_bundle). */
+unsigned int rsu_crc32c_host(unsigned int crc, const void* data_host, unsigned long long n);
+
 /* NHWC bf16 activation view: element (n, y, x, c) lives at ptr + n*sn + y*sy + x*sx + c. */
 typedef struct {
   const void* ptr;

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "rsu_version": (_i, []),
     "rsu_launch_count": (_ll, []),
     "rsu_reset_launch_count": (None, []),
+    "rsu_crc32c_host": (C.c_uint, [C.c_uint, _vp, _ull]),
     "rsu_conv_gemm": (_i, [C.POINTER(ConvGemmDesc), _vp]),
     "rsu_wgrad_gemm": (_i, [C.POINTER(WgradDesc), _vp]),
     "rsu_pack_transpose": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -145,7 +145,45 @@ int choose_ksplit(int mn_units, int k_tiles, int sms, double tile_cost, double u
 
 }  // namespace rsu
 
+namespace rsu {
+// CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), slicing-by-8 on the host.
+static uint32_t g_crc_tab[8][256];
+static std::once_flag g_crc_once;
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1) ? 0x82F63B78u : 0u);
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t)
+      g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xff];
+}
+}  // namespace rsu
+
 extern "C" {
+unsigned int rsu_crc32c_host(unsigned int crc, const void* data_host, unsigned long long n) {
+  std::call_once(rsu::g_crc_once, rsu::crc_init);
+  const unsigned char* p = static_cast<const unsigned char*>(data_host);
+  uint32_t c = ~crc;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) {
+    c = (c >> 8) ^ rsu::g_crc_tab[0][(c ^ *p++) & 0xff];
+    --n;
+  }
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = rsu::g_crc_tab[7][w & 0xff] ^ rsu::g_crc_tab[6][(w >> 8) & 0xff] ^
+        rsu::g_crc_tab[5][(w >> 16) & 0xff] ^ rsu::g_crc_tab[4][(w >> 24) & 0xff] ^
+        rsu::g_crc_tab[3][(w >> 32) & 0xff] ^ rsu::g_crc_tab[2][(w >> 40) & 0xff] ^
+        rsu::g_crc_tab[1][(w >> 48) & 0xff] ^ rsu::g_crc_tab[0][(w >> 56) & 0xff];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ rsu::g_crc_tab[0][(c ^ *p++) & 0xff];
+  return ~c;
+}
 const char* rsu_last_error(void) { return rsu::g_err; }
 int rsu_version(void) { return 100; }
 long long rsu_launch_count(void) { return rsu::g_launches.load(); }

@@ -20,6 +20,7 @@ import torch
 
 from . import images
 from . import unet
+from .summary import Summary
 from .constants import NUM_CHANNELS, IMG_PATCH_SIZE, FOREGROUND_THRESHOLD
 
 
@@ -156,6 +157,44 @@ def shared_window_jobs(num_images, windows, rank=0, world=1):
     return by_size
 
 
+def shard_pairs(num_images, angles, rank=0, world=1):
+    """The (angle, image) pairs of the training-set preparation (main, tf_aerial_images.py:403-423)
+    owned by `rank`: a contiguous slice of expand_and_rotate's angle-major output order, so that
+    concatenating the ranks' shards in rank order reproduces the unsharded tensor.  Returns
+    [(angle, [image indices])] with the images of one angle grouped."""
+    pairs = [(a, i) for a in angles for i in range(num_images)]
+    k0, k1 = shard_range(len(pairs), rank, world)
+    groups = []
+    for a, i in pairs[k0:k1]:
+        if groups and groups[-1][0] == a:
+            groups[-1][1].append(i)
+        else:
+            groups.append((a, [i]))
+    return groups
+
+
+def prepare_train_patches(train_images, train_groundtruth, opts, rank=0, world=1):
+    """The train-prep block of the reference's main (tf_aerial_images.py:403-423) for the
+    (angle, image) pairs one rank owns: expand_and_rotate + extract_patches of the images (input
+    size, offset border) and of the ground truth (patch size).  world = 1 is the reference's block
+    verbatim; with more ranks every rank prepares only the patches it will train on (SURVEY.md
+    8(e) row 3) and the union over ranks is the unsharded set, in the same order."""
+    input_size = unet.input_size_needed(opts.patch_size, opts.num_layers)
+    offset = int((input_size - opts.patch_size) / 2)
+    pats, labs = [], []
+    for angle, idx in shard_pairs(train_images.shape[0], opts.rotation_angles, rank, world):
+        extended_images = images.expand_and_rotate(train_images[idx], [angle], offset)
+        pats.append(images.extract_patches(extended_images, patch_size=input_size,
+                                           predict_patch_size=opts.patch_size, stride=opts.stride))
+        train_groundtruth_exp = images.expand_and_rotate(train_groundtruth[idx], [angle], 0)
+        labs.append(images.extract_patches(train_groundtruth_exp, patch_size=opts.patch_size,
+                                           stride=opts.stride))
+    if not pats:
+        return (np.zeros((0, input_size, input_size) + train_images.shape[3:]),
+                np.zeros((0, opts.patch_size, opts.patch_size)))
+    return np.concatenate(pats, axis=0), np.concatenate(labs, axis=0)
+
+
 def rank_batch_indices(indices, offset, rank, batch_size):
     """The slice of the (identically shuffled) epoch permutation that `rank` trains on at the
     global step starting at `offset`: ranks take consecutive batch_size-sized pieces."""
@@ -215,6 +254,14 @@ class ConvolutionalModel:
                                   (options.gpu if options.gpu >= 0 else 0))
         self._aug_rng = np.random.RandomState(options.seed + 7919 * self._dist.rank)
         self.scalars = []  # (step, loss, lr): what the reference sends to TensorBoard
+        # rank 0 writes <logdir>/<experiment_name>/scalars.jsonl (+ image dumps); every rank keeps
+        # the values in memory (tf_aerial_images.py:98-100)
+        summary_path = os.path.join(options.logdir, self.experiment_name)
+        self._summary = Summary(options, session, summary_path, write=self._dist.rank == 0)
+        # True when train() is handed only this rank's shard of the patches (main does that under
+        # torchrun): batches are then drawn from the local shard instead of a slice of the global
+        # permutation
+        self.sharded_data = False
         self.build_graph()
 
     # -- "graph": the planned engine --------------------------------------------------------
@@ -340,7 +387,7 @@ class ConvolutionalModel:
         self._graphs = (lr, gx, gy, g_fwd, g_bwd)
         return self._graphs
 
-    def train_batch(self, patches_batch, labels_batch):
+    def train_batch(self, patches_batch, labels_batch, copy_probs=True):
         """patches_batch [B,S,S,3], labels_batch [B,P,P] (host arrays).  Returns (loss, probs)."""
         opts = self._options
         net = self._net
@@ -395,13 +442,24 @@ class ConvolutionalModel:
         # the step's fetches (loss, probabilities) are what the caller waits for; the update that
         # follows them on the stream is ordered before everything the next call enqueues
         fetched.synchronize()
+        # (data parallel: the loss of this rank's slice of the global batch -- the step has ONE
+        # collective, the gradient all-reduce; mean_loss() averages the logged values on demand)
         loss = float(self._h_loss[0])
-        if self._dist.active:
-            t = torch.tensor([loss], device="cuda")
-            self._dist.dist.all_reduce(t)
-            loss = float(t.item()) / self._dist.world
         self.scalars.append((net.global_step, loss, lr))
-        return loss, self._h_probs.numpy()
+        # a fresh array per step, like session.run returns (the pinned fetch buffer is overwritten
+        # by the next step's copy); copy_probs=False hands out the buffer itself
+        probs = self._h_probs.numpy()
+        return loss, (probs.copy() if copy_probs else probs)
+
+    def mean_loss(self, last=1):
+        """Mean over ranks of the mean of the last `last` logged losses (one small all-reduce, on
+        demand -- not inside the training step)."""
+        v = float(np.mean([s[1] for s in self.scalars[-last:]])) if self.scalars else 0.0
+        if self._dist.active:
+            t = torch.tensor([v], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+            self._dist.dist.all_reduce(t)
+            v = float(t.item()) / self._dist.world
+        return v
 
     def train(self, patches, labels_patches, imgs, labels):
         """Train the model for one epoch (tf_aerial_images.py:212-269)."""
@@ -418,11 +476,21 @@ class ConvolutionalModel:
 
         num_errors = 0
         total = 0
-        gb = opts.batch_size * world  # global batch: every rank takes its own slice of it
-        offsets = list(range(0, num_train_patches - gb, gb))
+        if self.sharded_data and world > 1:
+            # `patches` is this rank's shard (prepare_train_patches): every rank walks its own
+            # shuffled shard; the step count follows the reference's rule on the smallest shard so
+            # that all ranks run the same number of collective steps
+            t = torch.tensor([num_train_patches], device="cuda" if torch.cuda.is_available() else "cpu")
+            self._dist.dist.all_reduce(t, op=self._dist.dist.ReduceOp.MIN)
+            offsets = list(range(0, int(t.item()) - opts.batch_size, opts.batch_size))
+            pick_rank = 0
+        else:
+            gb = opts.batch_size * world  # global batch: every rank takes its own slice of it
+            offsets = list(range(0, num_train_patches - gb, gb))
+            pick_rank = rank
 
         def host_batch(offset):
-            idx = rank_batch_indices(indices, offset, rank, opts.batch_size)
+            idx = rank_batch_indices(indices, offset, pick_rank, opts.batch_size)
             return idx, patches[idx, :, :, :], labels_patches[idx]
 
         nxt = host_batch(offsets[0]) if offsets else None
@@ -432,22 +500,35 @@ class ConvolutionalModel:
             nxt = host_batch(offsets[batch_i + 1]) if batch_i + 1 < len(offsets) else None
             if nxt is not None:
                 self.prefetch(nxt[1], nxt[2])
-            l, predictions = self.train_batch(pb, lb)
+            l, predictions = self.train_batch(pb, lb, copy_probs=False)
             step = self._net.global_step
             print("Batch {} Step {}".format(batch_i, step), end="\r")
+            self._summary.add({"loss": l, "learning_rate": self.scalars[-1][2]}, global_step=step)
 
             num_errors += np.abs(labels_patches[batch_indices] - predictions).sum()
             total += opts.batch_size
             self.misclassification = (num_errors, total)
+            self._summary.add_to_pixel_missclassification_summary(num_errors, total, step)
 
             # from time to time do full prediction on some images
             if step > 0 and step % opts.eval_every == 0:
                 print()
+
                 images_to_predict = imgs[:opts.num_eval_images, :, :, :]
-                self.last_eval_masks = self.predict(images_to_predict)
+                masks = self.predict(images_to_predict)
+                self.last_eval_masks = masks
+                overlays = images.overlays(images_to_predict, masks)
+                pred_masks = ((masks > 0.5) * 1).squeeze(-1)
+                true_masks = labels[:opts.num_eval_images, :, :]
+
+                self.last_eval_scores = self._summary.add_to_eval_summary(masks, overlays, labels, step)
+                self._summary.add_to_overlap_summary(true_masks, pred_masks, step)
 
             if step > 0 and step % opts.train_score_every == 0:
                 self.last_train_masks = self.predict(imgs)
+                self.last_train_scores = self._summary.add_to_training_summary(self.last_train_masks, labels, step)
+
+        self._summary.flush()
 
     # -- sliding-window prediction (tf_aerial_images.py:271-328) -----------------------------
     def predict(self, imgs):
@@ -528,19 +609,18 @@ class ConvolutionalModel:
         return part / self._overlap_counts(part.shape[1], side)
 
     def _shared_net(self, big_input, big_batch):
-        """forward-only engine for enlarged windows, weights copied from the training engine"""
+        """Forward-only engine for enlarged windows.  It aliases the training engine's master and
+        packed weights (no second copy, no random init, no repack) and is cached by window size
+        alone: the first request fixes its batch, later requests run on it whatever their batch
+        (predict() pads a short chunk with stale windows whose outputs are dropped)."""
         opts = self._options
         nets = self.__dict__.setdefault("_shared_nets", {})
-        key = (big_input, big_batch)
-        if key not in nets:
-            while len(nets) >= 2:  # their activations are the big allocations: keep two sizes
+        if big_input not in nets:
+            while len(nets) >= 4:  # activations are the big allocations: keep at most four sizes
                 nets.pop(next(iter(nets)))
-            nets[key] = unet.UNet(opts.num_layers, opts.root_size, opts.dilated_layers, big_batch,
-                                  big_input, seed=opts.seed, training=False)
-        big = nets[key]
-        big.params.copy_(self._net.params)
-        big.pack_weights()
-        return big
+            nets[big_input] = unet.UNet(opts.num_layers, opts.root_size, opts.dilated_layers, big_batch,
+                                        big_input, seed=opts.seed, training=False, weights_from=self._net)
+        return nets[big_input]
 
     def _predict_shared(self, x, num_images, side, plan):
         """Aligned windows evaluated once (shared_window_plan): each forward pass covers up to
@@ -574,6 +654,7 @@ class ConvolutionalModel:
                 win_b = max(1, int(B * S * S / (win_in * win_in)))
                 win_b = -(-len(group) // -(-len(group) // win_b))
                 net = self._shared_net(win_in, win_b)
+                win_b = net.B
             assert net.P == win_out and (Hz - win_in) % stride == 0
             side_z = (Hz - win_in) // stride + 1
             batch = torch.empty(win_b, win_in, win_in, NUM_CHANNELS, dtype=torch.float32, device="cuda")
@@ -621,7 +702,11 @@ class ConvolutionalModel:
 
     def save_to(self, model_data_dir):
         """The checkpoint write behind save(); also used for the '<save_dir>-model.chkpt' copy
-        of a submission run (tf_aerial_images.py:461)."""
+        of a submission run (tf_aerial_images.py:461).  Written as a TensorFlow V2 checkpoint
+        bundle (<path>.index + <path>.data-00000-of-00001, tf_checkpoint.write_bundle) -- the
+        files tf.train.Saver writes for the reference and can restore -- plus the <path>.meta
+        marker the reference's restore() globs for."""
+        from . import tf_checkpoint
         opts = self._options
         if self._dist.rank == 0:
             os.makedirs(os.path.dirname(model_data_dir), exist_ok=True)
@@ -631,8 +716,7 @@ class ConvolutionalModel:
             for k, v in self._net.state_dict("momentum").items():
                 payload[k + "/Momentum"] = v
             payload["global_step"] = np.array(self._net.global_step, dtype=np.int32)
-            with open(model_data_dir, "wb") as f:
-                np.savez(f, **payload)
+            tf_checkpoint.write_bundle(model_data_dir, payload)
             with open(model_data_dir + ".meta", "w") as f:
                 f.write("rsu_b200 checkpoint; num_layers={} root_size={} dilated_layers={}\n".format(
                     opts.num_layers, opts.root_size, opts.dilated_layers))
@@ -667,11 +751,25 @@ class ConvolutionalModel:
                 model_data_dir = os.path.abspath(
                     os.path.join(model_data_dir, 'model-epoch-{:03d}.chkpt'.format(epoch)))
 
-        with np.load(model_data_dir) as z:
-            params = {k: z[k] for k in z.files if not k.endswith("/Momentum") and k != "global_step"}
-            mom = {k[:-len("/Momentum")]: z[k] for k in z.files if k.endswith("/Momentum")}
-            step = int(z["global_step"]) if "global_step" in z.files else 0
-        self._net.load_state(params, mom)
+        from . import tf_checkpoint
+        if tf_checkpoint.is_bundle(model_data_dir):
+            # a TensorFlow V2 checkpoint: this engine's own save() or the reference's tf.train.Saver
+            # (same variable names and layouts, momentum slots under <name>/Momentum)
+            tensors = tf_checkpoint.read_bundle(model_data_dir)
+        elif os.path.isfile(model_data_dir):
+            with np.load(model_data_dir) as z:  # round-1 .npz payload
+                tensors = {k: z[k] for k in z.files}
+        else:
+            raise FileNotFoundError(
+                "no checkpoint at {0}: expected {0}.index + {0}.data-00000-of-00001 (TensorFlow V2 "
+                "bundle, written by save() and by the reference's Saver)".format(model_data_dir))
+        known = ("global_step", "beta1_power", "beta2_power")
+        params = {k: v for k, v in tensors.items() if not k.endswith("/Momentum") and k not in known}
+        mom = {k[:-len("/Momentum")]: v for k, v in tensors.items() if k.endswith("/Momentum")}
+        step = int(tensors["global_step"]) if "global_step" in tensors else 0
+        # strict: every variable of the architecture must be in the file with its exact shape and
+        # nothing unknown may be (a mismatched checkpoint must not leave random-init layers behind)
+        self._net.load_state(params, mom if mom else None, strict=True)
         self._net.global_step = step
         self._net.pack_weights()
         print("Model restored from from file: {}".format(model_data_dir))
@@ -695,26 +793,22 @@ def main(argv=None):
     if opts.num_epoch > 0:
         train_images, train_groundtruth = images.load_train_data(opts.train_data_dir)
 
-        input_size = unet.input_size_needed(opts.patch_size, opts.num_layers)
-        offset = int((input_size - opts.patch_size) / 2)
-        extended_images = images.expand_and_rotate(train_images, opts.rotation_angles, offset)
-        patches = images.extract_patches(extended_images,
-                                         patch_size=input_size,
-                                         predict_patch_size=opts.patch_size,
-                                         stride=opts.stride)
+        # every rank prepares only the (angle, image) pairs it will train on; one process: the
+        # reference's block (expand_and_rotate + extract_patches of images and ground truth)
+        dist_ = model._dist
+        patches, labels_patches = prepare_train_patches(train_images, train_groundtruth, opts,
+                                                        dist_.rank, dist_.world)
+        model.sharded_data = dist_.world > 1
 
         print("Train on {} patches of size {}x{}".format(patches.shape[0], patches.shape[1], patches.shape[2]))
-
-        train_groundtruth_exp = images.expand_and_rotate(train_groundtruth, opts.rotation_angles, 0)
-        labels_patches = images.extract_patches(train_groundtruth_exp,
-                                                patch_size=opts.patch_size,
-                                                stride=opts.stride)
 
         print("Train on {} groundtruth patches of size {}x{}".format(
             labels_patches.shape[0], labels_patches.shape[1], labels_patches.shape[2]))
 
+        model._summary.add_to_eval_patch_summary(train_groundtruth)
         for i in range(opts.num_epoch):
             print("==== Train epoch: {} ====".format(i))
+            model._summary.reset()  # Reset scores (tf.local_variables_initializer, :428)
             model.train(patches, labels_patches, train_images, train_groundtruth)  # Process one epoch
             model.save(i)  # Save model to disk
 

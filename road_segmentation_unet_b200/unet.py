@@ -105,9 +105,19 @@ class UNet:
     """
 
     def __init__(self, num_layers, root_size, dilated_layers, batch_size, input_size,
-                 device="cuda", seed=2017, training=True, params=None):
-        if root_size % 64 != 0:
-            raise ValueError("root_size must be a multiple of 64 (tcgen05 K chunk); got %d" % root_size)
+                 device="cuda", seed=2017, training=True, params=None, weights_from=None):
+        """params: dict name -> array (TensorFlow names / layouts); None = glorot init; {} = leave
+        the weights zero (a checkpoint follows).  weights_from: a donor UNet of the same
+        architecture whose master and packed weights this forward-only engine aliases (enlarged
+        prediction windows: no second copy of the weights, no repack)."""
+        if root_size not in (64, 128, 256):
+            # the head kernel (rsu_head) is instantiated for 64 / 128 / 256 input channels and the
+            # tcgen05 K chunk is 64 channels: anything else would only fail at the first forward
+            raise ValueError("root_size must be 64, 128 or 256 on this engine; got %d" % root_size)
+        if weights_from is not None:
+            d = weights_from
+            assert not training and (d.L, d.root, d.dilated) == (num_layers, root_size, bool(dilated_layers))
+        self._donor = weights_from
         if not torch.cuda.is_available():
             raise RuntimeError("the B200 U-Net engine needs a CUDA device; there is no CPU fallback")
         self.L, self.root, self.dilated = num_layers, root_size, bool(dilated_layers)
@@ -169,11 +179,15 @@ class UNet:
             off += (int(np.prod(shape)) + 63) // 64 * 64  # keep every variable 256-byte aligned
         self.n_flat = off
         dev = self.device
+        if self._donor is not None:
+            assert self._donor.n_flat == off
+            self.params, self.grads, self.momentum = self._donor.params, None, None
+            return
         self.params = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
         self.momentum = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
         init = params if params is not None else glorot_init(self.L, self.root, self.dilated, self.seed)
-        self.load_state(init)
+        self.load_state(init, strict=False)
 
     def _first_offset(self, prefix):
         for name, off in self.offsets.items():
@@ -197,8 +211,14 @@ class UNet:
         return enc, dec
 
     def _ready(self, bounds):
+        """A bucket of the flat gradient is final: hand its LIVE pieces to the data-parallel hook
+        (the dead conv_dilut_{L-1} range -- 27 % of the flagship's parameters -- never receives a
+        gradient and is not reduced)."""
         if self.on_bucket_ready is not None:
-            self.on_bucket_ready(bounds[0], bounds[1])
+            for a, b in self.live_ranges():
+                lo, hi = max(a, bounds[0]), min(b, bounds[1])
+                if hi > lo:
+                    self.on_bucket_ready(lo, hi)
 
     def var(self, name, which="params"):
         flat = getattr(self, which)
@@ -206,13 +226,28 @@ class UNet:
         o = self.offsets[name]
         return flat[o:o + int(np.prod(shape))].view(shape)
 
-    def load_state(self, params, momentum=None):
-        for name in self.shapes:
-            if name in params:
-                self.var(name).copy_(torch.as_tensor(np.asarray(params[name], dtype=np.float32)))
-            if momentum is not None and name in momentum and self.momentum is not None:
-                self.var(name, "momentum").copy_(
-                    torch.as_tensor(np.asarray(momentum[name], dtype=np.float32)))
+    def load_state(self, params, momentum=None, strict=True):
+        """Copy variables (and momentum slots) into the flat device vectors.  strict: every
+        variable of the architecture must be present with its exact shape and nothing else may be
+        (a partial or mismatched checkpoint must not restore silently with random-init layers)."""
+        if strict:
+            missing = [n for n in self.shapes if n not in params]
+            unexpected = [n for n in params if n not in self.shapes]
+            if missing or unexpected:
+                raise ValueError("checkpoint does not match the model (num_layers=%d root_size=%d "
+                                 "dilated_layers=%s): missing %s, unexpected %s"
+                                 % (self.L, self.root, self.dilated, missing[:4], unexpected[:4]))
+        for src, which in ((params, "params"), (momentum, "momentum")):
+            if src is None or getattr(self, which) is None:
+                continue
+            for name in self.shapes:
+                if name not in src:
+                    continue
+                a = np.asarray(src[name], dtype=np.float32)
+                if tuple(a.shape) != tuple(self.shapes[name]):
+                    raise ValueError("variable %s: checkpoint shape %s, model shape %s"
+                                     % (name, tuple(a.shape), tuple(self.shapes[name])))
+                self.var(name, which).copy_(torch.as_tensor(a))
 
     def state_dict(self, which="params"):
         return OrderedDict((n, self.var(n, which).detach().cpu().numpy().copy()) for n in self.shapes)
@@ -304,6 +339,9 @@ class UNet:
         self._drop_net = [None] * max(L - 1, 0)
         # packed bf16 weights
         self.convs = OrderedDict()
+        if self._donor is not None:
+            self.convs = self._donor.convs
+            return
         for name, shape in self.shapes.items():
             if not name.endswith("kernel") or name.startswith(("color_space", "weight_output")):
                 continue
@@ -353,6 +391,8 @@ class UNet:
     def pack_weights(self):
         """fp32 master (TensorFlow layouts) -> bf16 GEMM operand layouts; run after every update:
         one table-driven launch for all repacks plus the two folded first-layer kernels."""
+        if self._donor is not None:
+            return  # the donor's packed operands are this engine's
         if getattr(self, "_pack_plan", None) is None:
             self._pack_plan = ops.PackPlan(self._pack_jobs(), self.device)
         self._pack_plan.run()

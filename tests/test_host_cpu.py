@@ -17,7 +17,7 @@ def test_library_exports_header_symbols():
     from road_segmentation_unet_b200 import _lib
     lib = _lib.load()  # no compute calls: loading must work without a GPU
     header = open(os.path.join(ROOT, "include", "rsu_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|void|long long|const char\*)\s+(rsu_[a-z0-9_]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^(?:unsigned int|int|void|long long|const char\*)\s+(rsu_[a-z0-9_]+)\s*\(", header, re.M))
     assert len(declared) >= 25
     for name in sorted(declared):
         assert hasattr(lib, name), "librsu_b200.so does not export %s" % name
@@ -174,6 +174,82 @@ def test_shard_helpers():
     idx = np.arange(100)
     got = [tfa.rank_batch_indices(idx, 32, r, 8).tolist() for r in range(4)]
     assert sum(got, []) == list(range(32, 64))
+
+
+def test_shard_pairs_cover_the_training_set():
+    """every rank prepares only its (angle, image) pairs; the shards of all
+    ranks, concatenated in rank order, are expand_and_rotate's angle-major order exactly once."""
+    from road_segmentation_unet_b200 import tf_aerial_images as tfa
+    for n_img, angles in ((100, [15, 30, 45, 60, 75]), (3, [0, 90]), (10, [0]), (1, [15, 30, 45])):
+        full = [(a, i) for a in angles for i in range(n_img)]
+        for world in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(world):
+                for angle, idx in tfa.shard_pairs(n_img, angles, r, world):
+                    assert idx == sorted(idx) and len(idx) >= 1
+                    got.extend((angle, i) for i in idx)
+            assert got == full, (n_img, angles, world)
+            sizes = [sum(len(idx) for _, idx in tfa.shard_pairs(n_img, angles, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_streaming_metrics_match_tf_metrics_semantics():
+    """summary.py:141-147 / tf_aerial_images.py:428: tf.metrics.* accumulate counts over calls and
+    are zeroed once per epoch; F1 = 2 / (1/recall + 1/precision); the zero entries the reference
+    appends through ndarray.resize inflate the accuracy only."""
+    from road_segmentation_unet_b200.summary import StreamingMetrics
+    m = StreamingMetrics()
+    acc, rec, prec, f1 = m.update([1, 1, 0, 0, 1], [1, 0, 0, 1, 1])
+    assert (acc, rec, prec) == (0.6, 2 / 3, 2 / 3) and abs(f1 - 2 / 3) < 1e-12
+    acc, rec, prec, f1 = m.update([1, 0, 0], [1, 0, 1])      # running totals: 8 labels, tp 3, fn 1, fp 2
+    assert acc == 5 / 8 and rec == 3 / 4 and prec == 3 / 5
+    assert abs(f1 - 2 / (4 / 3 + 5 / 3)) < 1e-12
+    m.reset()
+    assert m.update([0, 0], [0, 1]) == (0.5, 0.0, 0.0, 0.0)   # 1/0 -> inf -> F1 0 like TensorFlow
+    m.reset()
+    acc, rec, prec, f1 = m.update([1, 0], [1, 1], padded_zeros=2 * 255)
+    assert acc == (1 + 510) / 512 and rec == 1.0 and prec == 0.5
+
+
+def test_tf_checkpoint_bundle_round_trip(tmp_path):
+    """TensorFlow V2 checkpoint bundle writer / importer (tf.train.Saver's files,
+    tf_aerial_images.py:343-379): table magic, masked CRC-32C known answers, multi-block index,
+    scalars, every dtype the model stores; corruption is detected."""
+    from road_segmentation_unet_b200 import tf_checkpoint as T
+    assert T.crc32c(b"123456789") == 0xE3069283                     # CRC-32C check value
+    assert T.crc32c(b"") == 0 and T.crc32c(b"6789", T.crc32c(b"12345")) == 0xE3069283
+    assert T.crc32c(bytes(32)) == 0x8A9136AA                         # RFC 3720 B.4 test vector
+    assert T.mask_crc(0) == 0xA282EAD8
+    rs = np.random.RandomState(0)
+    t = {"conv_0/conv1/kernel": rs.rand(3, 3, 3, 64).astype(np.float32),
+         "conv_0/conv1/kernel/Momentum": rs.rand(3, 3, 3, 64).astype(np.float32),
+         "global_step": np.array(1234, np.int32), "d": rs.rand(5), "i": np.arange(7, dtype=np.int64)}
+    for i in range(6000):  # > 256 KiB of index entries: several data blocks + restart points
+        t["scope_%05d/bias" % i] = rs.rand(3).astype(np.float32)
+    prefix = str(tmp_path / "model-epoch-003.chkpt")
+    T.write_bundle(prefix, t)
+    assert T.is_bundle(prefix) and os.path.exists(prefix + ".data-00000-of-00001")
+    raw = open(prefix + ".index", "rb").read()
+    assert raw[-8:] == bytes.fromhex("57fb808b247547db")            # LevelDB table magic, little endian
+    assert len(T.read_table(prefix + ".index")) == len(t) + 1      # + the header entry under ""
+    back = T.read_bundle(prefix)
+    assert set(back) == set(t)
+    for k in t:
+        assert back[k].dtype == t[k].dtype and back[k].shape == np.asarray(t[k]).shape, k
+        assert np.array_equal(back[k], t[k]), k
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[100] ^= 1
+    open(prefix + ".data-00000-of-00001", "wb").write(data)
+    with pytest.raises(ValueError, match="checksum"):
+        T.read_bundle(prefix)
+    idx = bytearray(raw)
+    idx[50] ^= 1
+    open(prefix + ".index", "wb").write(idx)
+    with pytest.raises(ValueError, match="checksum"):
+        T.read_table(prefix + ".index")
+    with pytest.raises(ValueError, match="magic"):
+        open(prefix + ".index", "wb").write(b"\0" * 64)
+        T.read_table(prefix + ".index")
 
 
 def _free_port():

@@ -125,14 +125,16 @@ def test_train_step_parity(case):
     floor = {n: rel(grads16[n], grads32[n]) for n in live}
     print("gradients vs fp32 oracle, worst:", sorted(e32.items(), key=lambda kv: -kv[1])[:4])
     print("bf16-storage oracle vs fp32 oracle (floor), worst:", sorted(floor.items(), key=lambda kv: -kv[1])[:4])
-    # the device is as close to fp32 as the bf16-storage oracle is (both are independent samples
-    # of the same flip noise, so compare the averages, not layer by layer)
-    assert max(e32.values()) < 0.25, max(e32.values())
+    # Per layer: within the 2e-2 gate of the fp32 oracle, or -- where max-pool arg-max / ReLU
+    # flips of near-ties dominate (few pixels: the deep levels at batch 1) -- no further from
+    # fp32 than twice what the bf16-storage ORACLE itself is on that layer (both are
+    # independent samples of the same flip noise).  test_flagship_free_running_batch4 holds the
+    # production architecture to the plain 2e-2 gate with the noise averaged over 4 patches.
+    bad = {n: (e32[n], floor[n]) for n in live if not (e32[n] < TOL or e32[n] < 2.0 * floor[n] + 5e-3)}
+    assert not bad, bad
     if P >= 128 and L <= 4:
         # at the full size of BASELINE.json configs[0] the flip noise averages out: every weight
         # gradient of the free-running backward pass is within the 2e-2 gate of the fp32 oracle
-        # (the 16^2-pixel bottom of the 6-level net at batch 1 stays flip-dominated, like the
-        # bf16-storage oracle itself: see the floor printed above)
         assert max(e32.values()) < TOL, sorted(e32.items(), key=lambda kv: -kv[1])[:4]
     assert np.mean(list(e32.values())) < 2.0 * np.mean(list(floor.values())) + 1e-2
 
@@ -191,7 +193,11 @@ def test_forward_api_logits():
     assert rel(logits, ref) < TOL
 
 
-@pytest.mark.parametrize("case", [(3, 64, True, 36, 2), (4, 64, True, 52, 1), (3, 64, False, 20, 2)])
+@pytest.mark.parametrize("case", [(3, 64, True, 36, 2), (4, 64, True, 52, 1), (3, 64, False, 20, 2),
+                                  # the production layer shapes (BASELINE.json configs[1..3]): CTA-pair
+                                  # kernel at Cout 1024 / 2048, resident-weight halo kernel with the fused
+                                  # pool at 760^2, split-K weight gradients over 760^2 pixels
+                                  (6, 64, True, 388, 1)])
 def test_backward_per_layer_teacher_forced(case):
     """Per-layer gradient parity inside the real network (the 2e-2 gate of BASELINE.json): every
     layer's backward kernels are fed the ORACLE's incoming gradient (bf16-storage oracle, masked
@@ -399,3 +405,37 @@ def test_backward_per_layer_teacher_forced(case):
     print("teacher-forced per-layer errors, worst:", sorted(report.items(), key=lambda kv: -kv[1])[:8])
     assert not failures, failures
     assert len(report) >= 8 * L
+
+
+def test_flagship_free_running_batch4():
+    """The production architecture (L=6, root 64, dilated, 764^2 -> 388^2) at batch 4, free-running
+    forward + backward against the reference's precision (fp32 oracle), 2e-2 relative per tensor:
+    every activation, the loss, and the weight / bias gradient of every layer above the bottom
+    block.  The bottom block (conv_5/*, 18^2 / 16^2 pixels per patch, and up_conv_0 that reads it)
+    is reported and held to the floor the bf16-storage oracle itself shows against fp32 there:
+    with ~1 k pixels per channel a single max-pool arg-max flip moves those gradients by percent."""
+    from road_segmentation_unet_b200 import unet
+    L, root, dil, P, B = 6, 64, True, 388, 4
+    S = unet.input_size_needed(P, L)
+    params = make_params(L, root, dil)
+    X, labels = synth(B, S, P, seed=77)
+    accs = {k: np.zeros_like(v) for k, v in params.items()}
+    loss32, probs32, grads32, _, _, _ = O.train_step(X, labels, params, accs, L, root, dil, 0.01, 0.9)
+    _, _, grads16, _, _, _ = O.train_step(X, labels, params, accs, L, root, dil, 0.01, 0.9, storage="bf16")
+    net = unet.UNet(L, root, dil, B, S, params=params)
+    net.grads.zero_()
+    net.forward(torch.tensor(X).cuda(), torch.tensor(labels).cuda(), keep=1.0)
+    net.backward()
+    torch.cuda.synchronize()
+    assert abs(net.loss.item() - loss32) < TOL * abs(loss32)
+    assert rel(net.probs.cpu().numpy(), probs32) < TOL
+    live = net.live_variables()
+    e32 = {n: rel(net.var(n, "grads").cpu().numpy(), grads32[n]) for n in live}
+    floor = {n: rel(grads16[n], grads32[n]) for n in live}
+    bottom = [n for n in live if n.startswith(("conv_%d/" % (L - 1), "up_conv_0/"))]
+    print("batch 4, gradients vs fp32 oracle, worst:", sorted(e32.items(), key=lambda kv: -kv[1])[:6])
+    print("bottom block:", {n: (round(e32[n], 4), round(floor[n], 4)) for n in bottom})
+    bad = {n: e32[n] for n in live if n not in bottom and not e32[n] < TOL}
+    assert not bad, bad
+    bad = {n: (e32[n], floor[n]) for n in bottom if not (e32[n] < TOL or e32[n] < 2.0 * floor[n] + 5e-3)}
+    assert not bad, bad

@@ -14,6 +14,7 @@ from oracle import images_oracle as IO
 from oracle import unet_oracle as O
 
 pytestmark = pytest.mark.gpu
+FLAGSHIP_TRAIN_STEPS = 60
 
 
 def blobs(rs, n, size, cells=6):
@@ -37,6 +38,7 @@ def make_model(tmp_path, **kw):
     opts.dropout, opts.lr, opts.momentum = 1.0, 0.02, 0.9
     opts.ensemble_prediction = True
     opts.save_path = str(tmp_path)
+    opts.logdir = str(tmp_path / "logdir")
     opts.eval_every = opts.train_score_every = 10 ** 9
     for k, v in kw.items():
         setattr(opts, k, v)
@@ -53,8 +55,9 @@ def oracle_predict(imgs, params, opts, S):
     tp = O.to_torch(params)
     preds = []
     with torch.no_grad():
-        for k in range(0, patches.shape[0], 16):
-            logits = O.forward(torch.tensor(patches[k:k + 16], dtype=torch.float32), tp,
+        step = 16 if S <= 256 else 3  # 764^2 windows: ~2 GB of fp32 activations per patch
+        for k in range(0, patches.shape[0], step):
+            logits = O.forward(torch.tensor(patches[k:k + step], dtype=torch.float32), tp,
                                opts.num_layers, opts.root_size, opts.dilated_layers)
             preds.append(torch.softmax(logits, dim=3)[..., 1].numpy())
     preds = np.concatenate(preds).astype(np.float64)
@@ -293,3 +296,153 @@ def test_stochastic_images_augmentation(tmp_path):
             assert np.array_equal(ma[b], O.d4_apply(m[b], flip[b], k[b]))
             seen[(bool(flip[b]), int(k[b]))] = seen.get((bool(flip[b]), int(k[b])), 0) + 1
     assert len(seen) == 8 and min(seen.values()) >= 15, seen  # 320 draws, 40 expected per element
+
+
+def test_flagship_predict_parity(tmp_path):
+    """BASELINE.json configs[2]'s model (run.py:122-132: 6 layers, dilated, 388^2 patches, 764^2
+    windows) through ConvolutionalModel.predict against the oracle pipeline (the reference's
+    predict(), tf_aerial_images.py:271-328, restated on the CPU): >= 99.5 % of the thresholded
+    pixels equal, patch-level F1 within 0.002.
+      * a 400^2 image at stride 12 with the 6-way ensemble -- the reference's training-image case,
+        4 windows x 6 variants, one forward pass per window;
+      * a 452^2 image at stride 32 (3 x 3 windows whose origins differ by the pooling period 32):
+        the shared-window path (one 828^2 pass covers all nine) AND the window loop, both against
+        the oracle's nine separate passes."""
+    model, opts = make_model(tmp_path, num_layers=6, patch_size=388, batch_size=2, stride=12, lr=0.01)
+    S = model.input_size
+    assert S == 764
+    off = (S - 388) // 2
+    rs = np.random.RandomState(0)
+    losses = []
+    for step in range(FLAGSHIP_TRAIN_STEPS):
+        lab = blobs(rs, 2, S, cells=12)
+        img = np.stack([0.25 + 0.5 * lab + 0.1 * rs.randn(2, S, S) for _ in range(3)], -1)
+        img[..., 1] = 0.5 + 0.1 * rs.randn(2, S, S)
+        img = np.clip(img, 0, 1).astype(np.float32)
+        losses.append(model.train_batch(img, lab[:, off:off + 388, off:off + 388])[0])
+    print("flagship training loss: first %.3f last %.3f" % (losses[0], np.mean(losses[-5:])))
+    assert np.mean(losses[-5:]) < 0.4 < losses[0], losses
+    params = model.net.state_dict()
+
+    def data(seed, size):
+        r = np.random.RandomState(seed)
+        lab = blobs(r, 1, size, cells=8)
+        img = np.stack([0.25 + 0.5 * lab + 0.1 * r.randn(1, size, size) for _ in range(3)], -1)
+        img[..., 1] = 0.5 + 0.1 * r.randn(1, size, size)
+        return np.clip(img, 0, 1).astype(np.float32), lab
+
+    def gate(tag, masks, ref, labels):
+        agree = float(((masks > 0.5) == (ref > 0.5)).mean())
+        f1_dev, f1_ref = IO.patch_f1(masks, labels[..., None]), IO.patch_f1(ref, labels[..., None])
+        print("%s: pixel agreement %.5f  max|dp| %.4f  mean|dp| %.5f  F1 device %.4f  oracle %.4f"
+              % (tag, agree, np.abs(masks - ref).max(), np.abs(masks - ref).mean(), f1_dev, f1_ref))
+        assert masks.shape == ref.shape and masks.dtype == np.float64
+        assert agree >= 0.995, (tag, agree)
+        assert abs(f1_dev - f1_ref) <= 0.002, (tag, f1_dev, f1_ref)
+        assert f1_ref > 0.5, (tag, f1_ref)  # a confident model, not p ~ 0.5 everywhere
+
+    # (1) 400^2, stride 12, ensemble: 2 x 2 windows per variant, nothing to share
+    imgs, labels = data(1, 400)
+    opts.ensemble_prediction, opts.stride, opts.shared_windows = True, 12, True
+    gate("400^2 stride 12 ensemble", model.predict(imgs), oracle_predict(imgs, params, opts, S), labels)
+
+    # (2) 452^2, stride 32, no ensemble: shared windows on and off against the same oracle masks
+    imgs, labels = data(2, 452)
+    opts.ensemble_prediction, opts.stride = False, 32
+    ref = oracle_predict(imgs, params, opts, S)
+    model.__dict__.pop("_shared_nets", None)
+    opts.shared_windows = True
+    shared = model.predict(imgs)
+    assert model.__dict__.get("_shared_nets"), "the shared-window path did not run"
+    gate("452^2 stride 32 shared windows", shared, ref, labels)
+    opts.shared_windows = False
+    gate("452^2 stride 32 window loop", model.predict(imgs), ref, labels)
+
+
+def test_eval_every_fires_streaming_metrics(tmp_path):
+    """SURVEY 8(f) row 3 (tf_aerial_images.py:247-267, :428; summary.py:104-147): the periodic
+    evaluation inside train() predicts num_eval_images images and feeds STREAMING patch metrics
+    (counts accumulate over evaluations, reset once per epoch); train_score_every does the same
+    on the whole training set; loss / learning rate / misclassification are logged every step."""
+    from road_segmentation_unet_b200 import images
+    from road_segmentation_unet_b200.summary import StreamingMetrics
+    model, opts = make_model(tmp_path, eval_every=2, train_score_every=3, num_eval_images=2,
+                             ensemble_prediction=False, logdir=str(tmp_path / "logs"))
+    S = model.input_size
+    off = (S - 36) // 2
+    rs = np.random.RandomState(4)
+    imgs, labs = make_data(rs, 3, 48)                       # (48 + 40 - 76) % 12 == 0; 16 | 48
+    pat, plab = make_data(rs, 24, S)
+    model._summary.reset()
+    model.train(pat.astype(np.float64), plab[:, off:off + 36, off:off + 36], imgs, labs)
+    steps = len(range(0, 24 - 4, 4))
+    assert model.global_step == steps == 5
+    tags = [t for t, _, _ in model._summary.scalars]
+    assert tags.count("loss") == tags.count("learning_rate") == tags.count("misclassification_rate") == steps
+    assert tags.count("eval f1_score") == 2 and tags.count("train f1_score") == 1   # steps 2, 4 / step 3
+    # the streamed values equal tf.metrics semantics replayed on the masks the evaluations produced
+    replay = StreamingMetrics()
+    pred = images.patch_labels(model.last_eval_masks, 16).reshape(-1)
+    true = images.patch_labels((labs[:2] >= 0.5) * 1., 16).reshape(-1)
+    got = [v for t, v, s in model._summary.scalars if t == "eval accuracy"]
+    assert len(got) == 2 and 0.0 <= got[-1] <= 1.0
+    # (second evaluation: counts of both evaluations; replaying the last one twice bounds it)
+    one = replay.update(true, pred, padded_zeros=pred.size * 255)
+    assert model._summary.eval_metrics.total == 2 * replay.total
+    assert abs(model.last_eval_scores[0] - got[-1]) < 1e-12
+    # per-epoch reset (main does it before every epoch)
+    model._summary.reset()
+    assert model._summary.eval_metrics.total == 0 and model._summary.train_metrics.total == 0
+    # the log file of rank 0 carries every scalar, image dumps exist
+    import json
+    rows = [json.loads(l) for l in open(tmp_path / "logs" / model.experiment_name / "scalars.jsonl")]
+    assert len(rows) == len(model._summary.scalars)
+    assert {r["tag"] for r in rows} >= {"loss", "learning_rate", "misclassification_rate", "eval accuracy",
+                                        "eval recall", "eval precision", "eval f1_score", "train f1_score"}
+    dumped = sorted(p.name for p in (tmp_path / "logs" / model.experiment_name / "images").iterdir())
+    assert any(n.startswith("eval_masks_000002") for n in dumped)
+    assert any(n.startswith("groundtruth_vs_prediction_000004") for n in dumped)
+
+
+def test_sharded_train_prep_and_strict_restore(tmp_path):
+    """(1) prepare_train_patches: the shards of all ranks, in rank order, are the reference's
+    train-prep block (expand_and_rotate + extract_patches of images and ground truth) exactly.
+    (2) restore() refuses checkpoints that do not match the architecture, and reads both the
+    TensorFlow bundle save() writes and the earlier .npz payload."""
+    from road_segmentation_unet_b200 import images, tf_aerial_images as tfa, tf_checkpoint
+    model, opts = make_model(tmp_path)
+    opts.rotation_angles = [0, 30, 90]
+    rs = np.random.RandomState(8)
+    imgs, labs = make_data(rs, 3, 48)
+    S = model.input_size
+    off = (S - 36) // 2
+    full_p = images.extract_patches(images.expand_and_rotate(imgs, opts.rotation_angles, off),
+                                    patch_size=S, predict_patch_size=36, stride=12)
+    full_l = images.extract_patches(images.expand_and_rotate(labs, opts.rotation_angles, 0),
+                                    patch_size=36, stride=12)
+    p1, l1 = tfa.prepare_train_patches(imgs, labs, opts)
+    assert np.array_equal(p1, full_p) and np.array_equal(l1, full_l)
+    for world in (2, 4):
+        parts = [tfa.prepare_train_patches(imgs, labs, opts, r, world) for r in range(world)]
+        assert np.array_equal(np.concatenate([p for p, _ in parts]), full_p)
+        assert np.array_equal(np.concatenate([l for _, l in parts]), full_l)
+        assert max(p.shape[0] for p, _ in parts) < full_p.shape[0]
+
+    path = model.save(1)
+    assert tf_checkpoint.is_bundle(path)
+    other, o2 = make_model(tmp_path, num_layers=4)
+    with pytest.raises(ValueError, match="does not match the model"):
+        other.restore(file=path)
+    t = tf_checkpoint.read_bundle(path)
+    assert int(t["global_step"]) == 0 and "conv_0/conv1/kernel/Momentum" in t
+    t["conv_0/conv2/bias"] = np.zeros(32, np.float32)
+    tf_checkpoint.write_bundle(str(tmp_path / "bad.chkpt"), t)
+    with pytest.raises(ValueError, match="conv_0/conv2/bias"):
+        model.restore(file=str(tmp_path / "bad.chkpt"))
+    with pytest.raises(FileNotFoundError, match="index"):
+        model.restore(file=str(tmp_path / "nothing.chkpt"))
+    # the round-1 .npz payload still restores
+    t = tf_checkpoint.read_bundle(path)
+    with open(tmp_path / "old.chkpt", "wb") as f:
+        np.savez(f, **t)
+    model.restore(file=str(tmp_path / "old.chkpt"))

@@ -39,6 +39,25 @@ UNIT = "patches/s"
 CFG = dict(num_layers=6, root_size=64, dilated_layers=True, patch_size=388, batch_size=32)
 
 
+def workload_config(B, world):
+    """`config` of the JSON line -- identical for the GPU arm and the reference arm."""
+    return {"workload": "U-Net num_layers=6 root_size=64 --dilated_layers, batch %d/GPU of "
+                        "764^2->388^2 patches, momentum SGD lr 0.01 mu 0.9, dropout 1.0 "
+                        "(BASELINE.json configs[1])" % B,
+            "global_batch": B * world, "parallelism": "dp%d" % world,
+            "l2": "inputs larger than L2 (>= 19 GB of activations per step)",
+            "timing": "CUDA events on the launch stream, max over ranks (reference arm: host clock)"}
+
+
+def host_threads():
+    """Cores this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers: the CPU
+    legs set the thread count themselves)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -125,8 +144,7 @@ def time_oracle(steps, warmup, threads=None):
     the SAME model, one 764^2 -> 388^2 patch per step, fp32."""
     import torch
     from oracle import unet_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     L, root, dil, P = CFG["num_layers"], CFG["root_size"], CFG["dilated_layers"], CFG["patch_size"]
     S = O.input_size_needed(P, L)
     params = O.init_params(L, root, dil, seed=2017)
@@ -154,24 +172,76 @@ def time_oracle(steps, warmup, threads=None):
     return 1.0 / float(np.mean(times)), float(np.mean(times)), torch.get_num_threads()
 
 
+def time_oracle_predict(n_forwards=4):
+    """CPU leg of the prediction half of the metric (SURVEY 8(d) "reference CPU path timed beside
+    it"): the oracle pipeline of ConvolutionalModel.predict on one synthetic 604^2 image, stride
+    12, 6-way ensemble.  The NumPy helpers run in full at config-3 sizes; of the 2,166 forward
+    passes of the L=6 dilated model a bounded sample is timed and extrapolated."""
+    import torch
+    from oracle import images_oracle as IO
+    from oracle import unet_oracle as O
+    torch.set_num_threads(host_threads())
+    L, root, dil, P = CFG["num_layers"], CFG["root_size"], CFG["dilated_layers"], CFG["patch_size"]
+    S = O.input_size_needed(P, L)
+    off = (S - P) // 2
+    img = np.random.RandomState(2017).rand(1, 604, 604, 3).astype(np.float32)
+    helpers = {}
+
+    def clock(name, nbytes, fn):
+        t0 = time.perf_counter()
+        out = fn()
+        dt = time.perf_counter() - t0
+        helpers[name] = {"seconds": dt, "gbs": nbytes / dt / 1e9, "alg_bytes": int(nbytes)}
+        return out
+
+    ens = clock("image_augmentation_ensemble", 7 * img.size * 8, lambda: IO.image_augmentation_ensemble(img))
+    pad = clock("mirror_border", (ens.size + 6 * 980 * 980 * 3) * 8, lambda: IO.mirror_border(ens, off))
+    # one variant's patch tensor (361 x 764^2 x 3 float64 = 5 GB); the six variants cost six times that
+    pat = clock("extract_patches", (980 * 980 * 3 + 361 * S * S * 3) * 8,
+                lambda: IO.extract_patches(pad[:1], S, stride=12, predict_patch_size=P))
+    tp = O.to_torch(O.init_params(L, root, dil, seed=2017))
+    x = torch.tensor(pat[:n_forwards + 1], dtype=torch.float32)
+    del pat
+    with torch.no_grad():
+        O.forward(x[:1], tp, L, root, dil)  # warm-up
+        t0 = time.perf_counter()
+        for k in range(n_forwards):
+            O.forward(x[k + 1:k + 2], tp, L, root, dil)
+        fwd_s = (time.perf_counter() - t0) / n_forwards
+    preds = np.random.RandomState(1).rand(6, 361, P, P, 1)
+    masks = clock("images_from_patches", (preds.size + 6 * 604 * 604) * 8,
+                  lambda: IO.images_from_patches(preds, stride=12))
+    clock("invert_image_augmentation_ensemble", 7 * 604 * 604 * 8,
+          lambda: IO.invert_image_augmentation_ensemble(masks))
+    n_fwd = 6 * 19 * 19
+    total = (helpers["image_augmentation_ensemble"]["seconds"] + helpers["mirror_border"]["seconds"]
+             + 6 * helpers["extract_patches"]["seconds"] + n_fwd * fwd_s
+             + helpers["images_from_patches"]["seconds"] + helpers["invert_image_augmentation_ensemble"]["seconds"])
+    return {"value": 604 * 604 / 1e6 / total, "unit": "Mpix/s", "seconds_per_image": total,
+            "patch_forwards_per_s": 1.0 / fwd_s, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "helpers in full (extract_patches: one of the 6 variants, x 6); %d of the %d forward passes "
+                      "of the L=6 dilated 764^2->388^2 model timed (fp32 torch-CPU oracle, %.2f s each), "
+                      "extrapolated" % (n_forwards, n_fwd, fwd_s),
+            "helpers": helpers}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, args.steps)
-    warmup = max(1, min(args.warmup, 2))
+    warmup = max(0, args.warmup)
     v, sec, threads = time_oracle(steps, warmup)
+    B = args.batch or CFG["batch_size"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "U-Net num_layers=6 root_size=64 --dilated_layers, batch 32/GPU of "
-                               "764^2->388^2 patches, momentum SGD lr 0.01 mu 0.9, dropout 1.0 "
-                               "(BASELINE.json configs[1])",
-                   "sample": "the CPU arm times batch 1 of that step (patches/s does not depend on the batch "
-                             "size on the CPU)"},
+        "config": workload_config(B, max(1, args.gpus)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d steps of batch 1 of the same model, fp32 torch-CPU oracle" % steps},
+                         "sample": "%d steps of batch 1 of the same model (patches/s does not depend on the "
+                                   "batch size on the CPU), fwd+bwd+momentum update, fp32 torch-CPU oracle on "
+                                   "%d host threads; rank 0 only" % (steps, threads)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -430,12 +500,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "U-Net num_layers=6 root_size=64 --dilated_layers, batch %d/GPU of "
-                                   "764^2->388^2 patches, momentum SGD lr 0.01 mu 0.9, dropout 1.0 "
-                                   "(BASELINE.json configs[1])" % B,
-                       "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "l2": "inputs larger than L2 (>= 19 GB of activations per step)",
-                       "timing": "CUDA events on the launch stream, max over ranks"},
+            "config": workload_config(B, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": ke, "api": "tf_aerial_images.ConvolutionalModel.prefetch + train_batch, as its epoch loop does "
                                         "(pinned host batch in, next batch's copy overlapped with the step, "

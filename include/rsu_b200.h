@@ -111,8 +111,8 @@ typedef struct {
                        return *bias_done tells whether the kernel produced it. */
   int* bias_done_host;
   int algo; /* 0 = choose, 1 = one TMA box per tap pair, 2 = halo tile shared by all taps,
-               3 = algorithm 1 on CTA pairs (EXPERIMENTAL, not validated on hardware; no bias
-               gradient; never chosen by 0) */
+               3 = algorithm 1 on CTA pairs (tcgen05.mma.cta_group::2; no bias gradient; chosen by 0
+               for 3x3 layers with >= 256 gradient channels and pixel grids up to 104^2) */
 } rsu_wgrad_desc;
 int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream);
 

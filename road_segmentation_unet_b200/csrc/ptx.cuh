@@ -158,6 +158,29 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Weight-stationary form (UTCHMMA.WS): the B operand goes through collector buffer b0 and can be
+// kept for the following instruction(s) that use the same B with another A, which are then spared
+// the shared-memory read of B.  USAGE: 0 = fill (read B, keep it), 1 = use (reuse, keep),
+// 2 = lastuse (reuse, release), 3 = discard (read B, do not keep).
+template <int USAGE>
+__device__ __forceinline__ void umma_ws_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                                  uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+#define RSU_WS_MMA(Q)                                                                         \
+  asm volatile(                                                                               \
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                           \
+      "setp.ne.b32 p, %6, 0;\n\t"                                                             \
+      "mov.b64 da, {%1, %2};\n\t"                                                             \
+      "mov.b64 db, {%3, %4};\n\t"                                                             \
+      "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::" Q " [%0], da, db, %5, p;\n\t}"    \
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)  \
+      : "memory")
+  if (USAGE == 0) RSU_WS_MMA("fill");
+  else if (USAGE == 1) RSU_WS_MMA("use");
+  else if (USAGE == 2) RSU_WS_MMA("lastuse");
+  else RSU_WS_MMA("discard");
+#undef RSU_WS_MMA
+}
 // hi word of a SWIZZLE_128B descriptor: stride byte offset, version 1, layout type 2
 __device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);

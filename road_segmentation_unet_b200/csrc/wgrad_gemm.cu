@@ -308,7 +308,7 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
     return set_error(RSU_EALIGN, "wgrad output must be 16-byte aligned");
 
   if (d->bias_done_host) *d->bias_done_host = 0;
-  // (thresholds from the per-layer A/B table, profiles/r1_layers_ab.md; the halo kernel also
+  // (thresholds from the per-layer A/B tables, profiles/r2_wgrad_pair_ab.txt; the halo kernel also
   // produces the bias gradient, which is counted in its favour)
   int chunks_all = 0;
   for (int s = 0; s < d->n_src && s < kMaxSrc; ++s) chunks_all += d->src[s].C / 64;
@@ -317,7 +317,7 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   const int max_chunks = (d->grad.C % 128 == 0) ? 6 : 4;
   const bool want_halo =
       d->algo == 2 || (d->algo == 0 && d->n_taps == 9 && d->H >= 64 && d->W >= 64 && chunks_all <= max_chunks &&
-                       (d->grad.C <= 128 || (d->grad.C <= 256 && d->H >= 180)));
+                       d->grad.C <= 128);
   if (want_halo) {
     int bias_done = 0;
     const int rc = launch_wgrad_halo(d, stream, &bias_done);
@@ -384,9 +384,13 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   p.out = d->out;
   p.ldo = d->ldo;
 
-  // experimental CTA-pair kernel (not validated on hardware yet: explicit request only); it has no
-  // ones atom, so the bias gradient is left to the caller (*bias_done_host stays 0)
-  if (d->algo == 3) return launch_wgrad_gemm2(p, stream);
+  // CTA-pair kernel (tcgen05.mma.cta_group::2, wgrad_gemm2.cu): each CTA of a pair loads half of
+  // the gradient tile.  Faster than the single-CTA kernel on every 3x3 layer with a 256-wide
+  // gradient tile and a small pixel grid (levels 3..8 of the flagship net: x1.00 - 1.11,
+  // profiles/r2_wgrad_pair_ab.txt).  It has no ones atom: the bias gradient of those layers (a
+  // pass over a few MB) is left to the caller (*bias_done_host stays 0).
+  if (d->algo == 3 || (d->algo == 0 && p.BN == 256 && d->n_taps == 9 && d->H <= 104 && d->W <= 104))
+    return launch_wgrad_gemm2(p, stream);
 
   const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
   const int mn_units = p.n_tiles_m * p.n_tiles_n;

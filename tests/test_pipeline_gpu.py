@@ -204,7 +204,9 @@ def test_main_train_eval_submission(tmp_path):
     conf = images.load(str(tmp_path / "dump"))  # all five dumps are RGBA files of the image size
     assert conf.shape == (20, 48, 48, 4)
     run_dir = tmp_path / "runs" / model.experiment_name
-    assert (run_dir / "model-epoch-000.chkpt").exists()
+    # a TensorFlow V2 bundle under the reference's naming, plus the .meta marker restore() globs for
+    for ext in (".index", ".data-00000-of-00001", ".meta"):
+        assert (run_dir / ("model-epoch-000.chkpt" + ext)).exists()
 
     model2 = tfa.main(common + ["--num_epoch=0", "--restore_model", "--eval_data_dir=" + str(tmp_path / "test")])
     out_dir = tmp_path / "runs" / model2.experiment_name
@@ -212,7 +214,7 @@ def test_main_train_eval_submission(tmp_path):
     assert rows[0] == "id,prediction" and len(rows) == 1 + 4 * 9
     assert rows[1].startswith("001_0_0,") and rows[4].startswith("001_16_0,") and rows[-1].startswith("004_32_32,")
     assert sorted(p.name for p in out_dir.glob("images_*.png")) == ["images_%03d.png" % i for i in range(1, 5)]
-    assert (tmp_path / "runs" / (model2.experiment_name + "-model.chkpt")).exists()
+    assert (tmp_path / "runs" / (model2.experiment_name + "-model.chkpt.index")).exists()
     # the restored model predicts what the trained one does, and the csv carries the 16 x 16 vote
     test_imgs = images.load(str(tmp_path / "test"))
     masks = model2.predict_batchwise(test_imgs, 2)

@@ -84,7 +84,10 @@ def run(n_img=24):
     padded = images.mirror_border_dev(x[:1], 188)
     out = torch.empty(128, 764, 764, 3, dtype=torch.float32, device="cuda")
     ms = timed(lambda: images.extract_patches_dev(padded, 764, 12, 0, 128, out=out))
-    add("extract_patches", 2 * out.numel() * 4, ms, "128 patches 764^2x3 fp32, stride 12 (reads hit L2)")
+    # algorithmic bytes: the padded source image once (it stays in L2 across the overlapping
+    # windows) + every patch element written once
+    add("extract_patches", (padded.numel() + out.numel()) * 4, ms,
+        "128 patches 764^2x3 fp32 out of one 980^2 image, stride 12: source read once + patches written once")
 
     preds = torch.rand(361, 388, 388, 1, device="cuda", generator=g)
     ms = timed(lambda: images.images_from_patches_dev(preds, 1, 19, 12))

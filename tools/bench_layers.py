@@ -73,7 +73,8 @@ def main():
     B = args.batch
     res = {}
     for name, srcs, cout, d, ho in layer_list():
-        if args.only and args.only not in name:
+        if args.only and not any(o == name or (o.endswith("*") and name.startswith(o[:-1]))
+                                 for o in args.only.split(",")):
             continue
         cin = sum(c for _, c, _ in srcs)
         xs = [torch.randn(B, e, e, c, device="cuda").to(torch.bfloat16) for e, c, _ in srcs]

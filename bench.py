@@ -283,8 +283,7 @@ def run_gpu(args):
         net.zero_grads()
         net.forward(x, lab, keep=1.0)
         net.backward()
-        scale = model._reducer.finish() if model._reducer is not None else 1.0
-        net.apply_gradients(opts.lr, opts.momentum, scale)
+        model.apply_update()
 
     W, K = max(args.warmup, 3), max(args.steps, 1)
     for _ in range(W):
@@ -304,6 +303,7 @@ def run_gpu(args):
     e1.record()
     barrier()
     launches = int(lib.rsu_launch_count())
+    launch_hist = {k: v / K for k, v in ops._lib.launch_histogram().items()}  # per step
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(net.loss.item())
@@ -348,6 +348,25 @@ def run_gpu(args):
     e2e_value = world * B * ke / e2e_s
     h2d = B * S * S * 3 * 4 + B * P * P
     d2h = B * P * P * 4 + 4
+    # the same loop with --image_augmentation (BASELINE.json configs[3]): every step additionally
+    # applies a random dihedral transform to the batch and its masks on the device (rsu_d4_transform)
+    opts.image_augmentation = True
+    model.train_batch(xp[0], lp[0])
+    barrier()
+    t0 = time.perf_counter()
+    model.prefetch(xp[0], lp[0])
+    for i in range(ke):
+        if i + 1 < ke:
+            model.prefetch(xp[(i + 1) % 2], lp[(i + 1) % 2])
+        model.train_batch(xp[i % 2], lp[i % 2])
+    torch.cuda.synchronize()
+    aug_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([aug_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        aug_s = float(t.item())
+    e2e_aug_value = world * B * ke / aug_s
+    opts.image_augmentation = False
 
     # ---- sliding-window ensemble prediction (BASELINE.json configs[2]) through the public API:
     # one synthetic 604^2 image, stride 12, 6-way flip/rot90 ensemble = 2,166 patch forwards of the
@@ -478,15 +497,27 @@ def run_gpu(args):
                                for r in res["kernels"]}}
         except Exception as e:  # the headline numbers above must survive a failure here
             hbm = {"error": repr(e)}
-    # DRAM traffic of the dominant kernel class per step, from the committed ncu pass
+    # DRAM traffic of the dominant kernel class per step, from the committed ncu pass of the same
+    # step -- accepted only if that capture saw the kernels this run launched (same names, same
+    # launches per step); a capture of another kernel mix is reported as stale, not as a number
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
-    if rank == 0 and os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f)
-        if roof is not None:
-            roof["traffic"] = traffic.get("conv_class_dram_bytes_per_step")
-            roof["traffic_source"] = traffic.get("source")
+    tpath = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
+    if rank == 0 and roof is not None:
+        conv_names = ("conv_gemm_kernel", "conv_gemm2_kernel", "conv_halo_kernel", "first_conv_kernel")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)
+            seen = {k: v["launches"] for k, v in traffic.get("by_kernel", {}).items() if k in conv_names}
+            ran = {k: int(round(v)) for k, v in launch_hist.items() if k in conv_names}
+            if seen == ran:
+                roof["traffic"] = traffic.get("conv_class_dram_bytes_per_step")
+                roof["traffic_source"] = traffic.get("source")
+            else:
+                roof["traffic"] = None
+                roof["traffic_source"] = "profiles/r2_step_traffic.json is stale: it holds %s, this run launched %s" \
+                    % (seen, ran)
+        else:
+            roof["traffic_source"] = "no ncu capture committed for this kernel mix"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -494,6 +525,11 @@ def run_gpu(args):
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "2 timed steps (after 1 warm-up) of batch 1 of the same L=6 dilated 764^2->388^2 "
                          "model, fwd+bwd+momentum update, fp32 torch-CPU oracle (%.1f s/step)" % sec}
+        if not args.no_predict:
+            try:  # prediction half of the metric + the NumPy helpers at config-3 sizes
+                cpu["predict"] = time_oracle_predict()
+            except Exception as e:
+                cpu["predict"] = {"error": repr(e)}
 
     if rank == 0:
         line = {
@@ -504,8 +540,17 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": ke, "api": "tf_aerial_images.ConvolutionalModel.prefetch + train_batch, as its epoch loop does "
                                         "(pinned host batch in, next batch's copy overlapped with the step, "
-                                        "loss + probabilities read back every step)"},
-            "gpu_launches": launches, "loss": loss_val, "clocks": clocks,
+                                        "loss + probabilities read back every step)",
+                    # the second half of the metric ("... & sliding-window predict Mpix/s") through
+                    # ConvolutionalModel.predict: host image in, host mask out, all ranks
+                    "predict": None if predict is None else {
+                        "value": predict["value"], "unit": "Mpix/s", "seconds": predict["seconds"],
+                        "window_loop_value": predict["window_loop"]["value"],
+                        "patch_forwards_per_s": predict["window_loop"]["patch_forwards_per_s"],
+                        "config": predict["config"]},
+                    # BASELINE.json configs[3]: the same loop with --image_augmentation
+                    "with_image_augmentation": {"value": e2e_aug_value, "unit": UNIT}},
+            "gpu_launches": launches, "launches_per_step": launch_hist, "loss": loss_val, "clocks": clocks,
             "roofline": roof, "cpu_baseline": cpu, "predict": predict, "hbm_kernels": hbm,
         }
         line.update(extra)

@@ -37,6 +37,10 @@ int rsu_version(void);
 /* Number of kernels launched by this library since load / since the last reset. */
 long long rsu_launch_count(void);
 void rsu_reset_launch_count(void);
+/* The same count per kernel, as "name=count;name=count;..." written into buf_host (at most cap
+ * bytes incl. the terminator); returns the size needed.  Lets the bench check that a committed ncu
+ * capture describes the kernels that actually ran. */
+int rsu_launch_histogram(char* buf_host, int cap);
 
 /* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum
  * TensorFlow's checkpoint bundle stores per tensor and per index block (tf.train.Saver,
@@ -206,6 +210,30 @@ int rsu_dropout_mask(float* m, long long n, float keep, unsigned long long seed,
  *   acc = momentum*acc + g*gscale ; w -= lr*acc */
 int rsu_momentum_sgd(float* w, float* acc, const float* g, long long n, float lr, float momentum,
                      float gscale, void* stream);
+
+/* Data-parallel optimizer step over NVLink peer memory (one process per GPU; replaces
+ * "all-reduce the flat gradient, then ApplyMomentum on every replica", tf_aerial_images.py:112-122):
+ * for the elements [begin, end) of the flat parameter vector -- the calling rank's slice --
+ *   g = sum_r grads[r][i] ; acc[i] = momentum*acc[i] + g*gscale ; w = params[rank][i] - lr*acc[i] ;
+ *   params[r][i] = w for every rank r.
+ * grads[r] / params[r]: device addresses of rank r's flat gradient / parameter buffers as mapped
+ * into THIS process (symmetric memory; entry `rank` is the local buffer).  grads_mc / params_mc:
+ * NVLS multicast addresses of the same buffers, or NULL (then plain peer loads / stores are used).
+ * The caller orders the step across ranks: every rank's gradients are final before the call, and
+ * no rank reads its parameters (or zeroes its gradients) before every rank's call has completed. */
+#define RSU_MAX_PEERS 8
+typedef struct {
+  int world, rank;
+  const float* grads[RSU_MAX_PEERS];
+  float* params[RSU_MAX_PEERS];
+  const float* grads_mc;
+  float* params_mc;
+} rsu_dp_peers;
+int rsu_dp_momentum_sgd(const rsu_dp_peers* peers, float* acc, long long begin, long long end, float lr,
+                        float momentum, float gscale, void* stream);
+
+/* Zero-fill of a device range on `stream` (gradient and loss accumulators before a step). */
+int rsu_fill_zero(void* ptr, long long bytes, void* stream);
 
 /* First-layer (Cin = 3) 3x3 convolution with the im2col operand generated on the fly
  * (color_space_adjust + dropout + conv_0/conv1 or conv_dilut_0/atrous_conv1, src/unet.py:22-23,

@@ -47,6 +47,14 @@ class PackJob(C.Structure):
                 ("R", C.c_int), ("C", C.c_int), ("ld", C.c_int)]
 
 
+RSU_MAX_PEERS = 8
+
+
+class DpPeers(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("grads", C.c_void_p * RSU_MAX_PEERS),
+                ("params", C.c_void_p * RSU_MAX_PEERS), ("grads_mc", C.c_void_p), ("params_mc", C.c_void_p)]
+
+
 class RsuError(RuntimeError):
     pass
 
@@ -61,6 +69,7 @@ _SIGNATURES = {
     "rsu_launch_count": (_ll, []),
     "rsu_reset_launch_count": (None, []),
     "rsu_crc32c_host": (C.c_uint, [C.c_uint, _vp, _ull]),
+    "rsu_launch_histogram": (_i, [C.c_char_p, _i]),
     "rsu_conv_gemm": (_i, [C.POINTER(ConvGemmDesc), _vp]),
     "rsu_wgrad_gemm": (_i, [C.POINTER(WgradDesc), _vp]),
     "rsu_pack_transpose": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -83,6 +92,8 @@ _SIGNATURES = {
     "rsu_dropout": (_i, [_vp, _vp, _ll, _f, _ull, _vp]),
     "rsu_dropout_mask": (_i, [_vp, _ll, _f, _ull, _vp]),
     "rsu_momentum_sgd": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
+    "rsu_dp_momentum_sgd": (_i, [C.POINTER(DpPeers), _vp, _ll, _ll, _f, _f, _f, _vp]),
+    "rsu_fill_zero": (_i, [_vp, _ll, _vp]),
     "rsu_mirror_pad": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rsu_d4_transform": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "rsu_extract_patches": (_i, [_vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp, _vp]),
@@ -99,9 +110,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    # (re)build when the sources changed since the .so was linked: a cheap digest check, so a stale
+    # library is never used silently after an edit of csrc/ (needs nvcc only when it has to build)
+    from . import build as _build
+    try:
         _build.build()
+    except Exception:
+        if not os.path.exists(LIB_PATH):
+            raise
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
@@ -138,3 +154,16 @@ def view(t, C_=None, c0=0, off_y=0, off_x=0):
 
 def launch_count():
     return load().rsu_launch_count()
+
+
+def launch_histogram():
+    """{kernel name: launches since the last reset}"""
+    lib = load()
+    buf = C.create_string_buffer(8192)
+    lib.rsu_launch_histogram(buf, len(buf))
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if "=" in item:
+            k, v = item.split("=")
+            out[k] = int(v)
+    return out

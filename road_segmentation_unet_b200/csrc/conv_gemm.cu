@@ -216,8 +216,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias_t[ch * 32 + j];
+            add_bias32(v, bias_t + ch * 32);
           }
           if (p.relu) {
 #pragma unroll

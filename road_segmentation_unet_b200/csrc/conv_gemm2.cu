@@ -278,8 +278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv2Threads, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias_t[ch * 32 + j];
+            add_bias32(v, bias_t + ch * 32);
           }
           if (p.relu) {
 #pragma unroll

@@ -425,8 +425,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(h == 0 ? r0[j] : r1[j]);
             if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += bias_t[cb * 64 + h * 32 + j];
+              add_bias32(v, bias_t + cb * 64 + h * 32);
             }
             if (p.relu) {
 #pragma unroll
@@ -551,8 +550,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += bias_t[ch * 32 + j];
+              add_bias32(v, bias_t + ch * 32);
             }
             if (p.relu) {
 #pragma unroll

@@ -8,6 +8,12 @@ namespace rsu {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+// launches per kernel name (the string literals handed to check_launch), for rsu_launch_histogram
+constexpr int kMaxNames = 64;
+static const char* g_names[kMaxNames];
+static long long g_name_counts[kMaxNames];
+static int g_n_names = 0;
+static std::mutex g_name_mu;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -22,6 +28,16 @@ int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(RSU_ECUDA, "%s: %s", what, cudaGetErrorString(e));
   count_launch();
+  {
+    std::lock_guard<std::mutex> lock(g_name_mu);
+    int i = 0;
+    while (i < g_n_names && g_names[i] != what && strcmp(g_names[i], what) != 0) ++i;
+    if (i == g_n_names && g_n_names < kMaxNames) {
+      g_names[g_n_names] = what;
+      g_name_counts[g_n_names++] = 0;
+    }
+    if (i < kMaxNames) ++g_name_counts[i];
+  }
   return RSU_OK;
 }
 
@@ -187,5 +203,22 @@ unsigned int rsu_crc32c_host(unsigned int crc, const void* data_host, unsigned l
 const char* rsu_last_error(void) { return rsu::g_err; }
 int rsu_version(void) { return 100; }
 long long rsu_launch_count(void) { return rsu::g_launches.load(); }
-void rsu_reset_launch_count(void) { rsu::g_launches.store(0); }
+void rsu_reset_launch_count(void) {
+  rsu::g_launches.store(0);
+  std::lock_guard<std::mutex> lock(rsu::g_name_mu);
+  for (int i = 0; i < rsu::g_n_names; ++i) rsu::g_name_counts[i] = 0;
+}
+int rsu_launch_histogram(char* buf_host, int cap) {
+  std::lock_guard<std::mutex> lock(rsu::g_name_mu);
+  int need = 1;
+  if (buf_host && cap > 0) buf_host[0] = 0;
+  for (int i = 0; i < rsu::g_n_names; ++i) {
+    if (rsu::g_name_counts[i] == 0) continue;
+    char item[160];
+    const int n = snprintf(item, sizeof(item), "%s=%lld;", rsu::g_names[i], rsu::g_name_counts[i]);
+    if (buf_host && need + n <= cap) strcat(buf_host, item);
+    need += n;
+  }
+  return need;
+}
 }

@@ -243,6 +243,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 }
 
 // ---------------------------------------------------------------- misc
+// v[0..31] += 32 consecutive floats of a 16-byte-aligned shared-memory array (generic pointer),
+// read as 8 x LDS.128: every warp-uniform 4-byte LDS is a wavefront of the shared-memory pipe the
+// tensor core's operand reads also go through, and the epilogues run while the MMAs do.
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* bias_smem) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias_smem);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = b4[q];
+    v[4 * q + 0] += b.x;
+    v[4 * q + 1] += b.y;
+    v[4 * q + 2] += b.z;
+    v[4 * q + 3] += b.w;
+  }
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -270,6 +270,12 @@ def dropout_mask(n, keep, seed, device="cuda"):
     return m
 
 
+def fill_zero(t):
+    """Zero a contiguous device tensor with a memset on the current stream (rsu_fill_zero)."""
+    assert t.is_contiguous()
+    call("rsu_fill_zero", _ptr(t), t.numel() * t.element_size())
+
+
 def momentum_sgd(w, acc, g, lr, momentum, gscale=1.0):
     call("rsu_momentum_sgd", _ptr(w), _ptr(acc), _ptr(g), w.numel(), float(lr), float(momentum),
          float(gscale))

@@ -265,10 +265,30 @@ class ConvolutionalModel:
         self.build_graph()
 
     # -- "graph": the planned engine --------------------------------------------------------
+    def _make_peer_optimizer(self):
+        """Data-parallel ranks on NVLink-connected GPUs exchange gradients and weights inside the
+        optimizer kernel (dp.PeerOptimizer).  RSU_DP_MODE = peer | nccl | auto (default: peer when
+        symmetric memory can be set up, else the bucketed NCCL all-reduce)."""
+        mode = os.environ.get("RSU_DP_MODE", "auto")
+        if not self._dist.active or not torch.cuda.is_available() or mode == "nccl":
+            return None
+        opts = self._options
+        try:
+            from .dp import PeerOptimizer
+            _, n_flat = unet.flat_layout(opts.num_layers, opts.root_size, opts.dilated_layers)
+            return PeerOptimizer(self._dist.dist, self._dist.world, self._dist.rank, n_flat)
+        except Exception as e:  # no peer access / symmetric memory unavailable
+            if mode == "peer":
+                raise
+            print("peer-memory optimizer unavailable ({}); using the NCCL all-reduce".format(e))
+            return None
+
     def build_graph(self):
         opts = self._options
+        self._peer = self._make_peer_optimizer()
+        flat = None if self._peer is None else {"params": self._peer.params, "grads": self._peer.grads}
         self._net = unet.UNet(opts.num_layers, opts.root_size, opts.dilated_layers, opts.batch_size,
-                              self.input_size, seed=opts.seed, training=True)
+                              self.input_size, seed=opts.seed, training=True, flat_buffers=flat)
         B, S, P = opts.batch_size, self.input_size, opts.patch_size
         assert self._net.P == P
         # two input slots: while a step computes from one, the next batch is staged (pinned host
@@ -284,7 +304,7 @@ class ConvolutionalModel:
         self._h_probs = torch.empty(B, P, P, dtype=torch.float32).pin_memory()
         self._h_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         self._reducer = GradientAllReducer(self._dist.dist, self._dist.world, self._net.grads) \
-            if self._dist.active else None
+            if self._dist.active and self._peer is None else None
         if self._reducer is not None:
             self._net.on_bucket_ready = self._reducer.bucket_ready
 
@@ -436,8 +456,7 @@ class ConvolutionalModel:
         free.record(cur)
         self._slot_free[self._slot] = free
         if graphs is None:
-            scale = self._reducer.finish() if self._reducer is not None else 1.0
-            net.apply_gradients(opts.lr, opts.momentum, scale)
+            self.apply_update()
             self._eager_steps = getattr(self, "_eager_steps", 0) + 1
         # the step's fetches (loss, probabilities) are what the caller waits for; the update that
         # follows them on the stream is ordered before everything the next call enqueues
@@ -450,6 +469,16 @@ class ConvolutionalModel:
         # by the next step's copy); copy_probs=False hands out the buffer itself
         probs = self._h_probs.numpy()
         return loss, (probs.copy() if copy_probs else probs)
+
+    def apply_update(self):
+        """The optimizer step that follows a backward pass: gradient exchange of the data-parallel
+        ranks + momentum update + global_step + operand repack."""
+        opts = self._options
+        if self._peer is not None:
+            self._net.apply_gradients(opts.lr, opts.momentum, peer=self._peer)
+        else:
+            scale = self._reducer.finish() if self._reducer is not None else 1.0
+            self._net.apply_gradients(opts.lr, opts.momentum, scale)
 
     def mean_loss(self, last=1):
         """Mean over ranks of the mean of the last `last` logged losses (one small all-reduce, on
@@ -708,13 +737,18 @@ class ConvolutionalModel:
         marker the reference's restore() globs for."""
         from . import tf_checkpoint
         opts = self._options
+        momentum = self._net.momentum
+        if self._peer is not None:  # every rank holds the momentum of its own slices only
+            momentum = self._peer.full_momentum(self._net)
         if self._dist.rank == 0:
             os.makedirs(os.path.dirname(model_data_dir), exist_ok=True)
             payload = {}
             for k, v in self._net.state_dict("params").items():
                 payload[k] = v
+            keep, self._net.momentum = self._net.momentum, momentum
             for k, v in self._net.state_dict("momentum").items():
                 payload[k + "/Momentum"] = v
+            self._net.momentum = keep
             payload["global_step"] = np.array(self._net.global_step, dtype=np.int32)
             tf_checkpoint.write_bundle(model_data_dir, payload)
             with open(model_data_dir + ".meta", "w") as f:

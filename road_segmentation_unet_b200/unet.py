@@ -88,6 +88,16 @@ def glorot_init(num_layers, root_size, dilated_layers, seed=2017):
     return out
 
 
+def flat_layout(num_layers, root_size, dilated_layers):
+    """Offsets of every variable inside the flat fp32 vectors (each 256-byte aligned) and their
+    total length: (OrderedDict name -> offset, n_flat)."""
+    offsets, off = OrderedDict(), 0
+    for name, shape in variable_shapes(num_layers, root_size, dilated_layers).items():
+        offsets[name] = off
+        off += (int(np.prod(shape)) + 63) // 64 * 64
+    return offsets, off
+
+
 class _Conv:
     """One 3x3 convolution of the plan: where its operands live and how it is wired."""
 
@@ -105,11 +115,14 @@ class UNet:
     """
 
     def __init__(self, num_layers, root_size, dilated_layers, batch_size, input_size,
-                 device="cuda", seed=2017, training=True, params=None, weights_from=None):
+                 device="cuda", seed=2017, training=True, params=None, weights_from=None,
+                 flat_buffers=None):
         """params: dict name -> array (TensorFlow names / layouts); None = glorot init; {} = leave
         the weights zero (a checkpoint follows).  weights_from: a donor UNet of the same
         architecture whose master and packed weights this forward-only engine aliases (enlarged
-        prediction windows: no second copy of the weights, no repack)."""
+        prediction windows: no second copy of the weights, no repack).  flat_buffers: {"params",
+        "grads"} fp32 device vectors of flat_layout()'s length to use instead of fresh allocations
+        (symmetric memory shared with the other data-parallel ranks, see dp.PeerOptimizer)."""
         if root_size not in (64, 128, 256):
             # the head kernel (rsu_head) is instantiated for 64 / 128 / 256 input channels and the
             # tcgen05 K chunk is 64 channels: anything else would only fail at the first forward
@@ -118,6 +131,7 @@ class UNet:
             d = weights_from
             assert not training and (d.L, d.root, d.dilated) == (num_layers, root_size, bool(dilated_layers))
         self._donor = weights_from
+        self._flat_buffers = flat_buffers
         if not torch.cuda.is_available():
             raise RuntimeError("the B200 U-Net engine needs a CUDA device; there is no CPU fallback")
         self.L, self.root, self.dilated = num_layers, root_size, bool(dilated_layers)
@@ -172,19 +186,19 @@ class UNet:
     def _alloc_state(self, params):
         shapes = variable_shapes(self.L, self.root, self.dilated)
         self.shapes = shapes
-        self.offsets = OrderedDict()
-        off = 0
-        for name, shape in shapes.items():
-            self.offsets[name] = off
-            off += (int(np.prod(shape)) + 63) // 64 * 64  # keep every variable 256-byte aligned
+        self.offsets, off = flat_layout(self.L, self.root, self.dilated)
         self.n_flat = off
         dev = self.device
         if self._donor is not None:
             assert self._donor.n_flat == off
             self.params, self.grads, self.momentum = self._donor.params, None, None
             return
-        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
+        if self._flat_buffers is not None:
+            self.params, self.grads = self._flat_buffers["params"], self._flat_buffers["grads"]
+            assert self.params.numel() == off == self.grads.numel() and self.params.dtype == torch.float32
+        else:
+            self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.grads = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
         self.momentum = torch.zeros(off, dtype=torch.float32, device=dev) if self.training else None
         init = params if params is not None else glorot_init(self.L, self.root, self.dilated, self.seed)
         self.load_state(init, strict=False)
@@ -490,7 +504,7 @@ class UNet:
             ops.head(net, wh, bh, probs=self.probs, logits=self.logits if want_logits else None)
         else:
             assert self.training
-            self.loss.zero_()
+            ops.fill_zero(self.loss)
             dlast = self.dC2[L - 2] if L > 1 else self.dA2[0]
             ops.head(net, wh, bh, labels=labels, probs=self.probs,
                      logits=self.logits if want_logits else None, loss=self.loss, dz=dlast,
@@ -530,7 +544,7 @@ class UNet:
         """Cin = 3 convolution through its im2col matrix, plus d(color_space_adjust)."""
         self._tag(conv.name)
         g = lambda n: self.var(conv.name + "/" + n, "grads")
-        conv.dw_stage.zero_()
+        ops.fill_zero(conv.dw_stage)
         if self.fused_first:
             drop = self._keep < 1.0
             cw = self.var("color_space_adjust/kernel") if drop else None
@@ -650,13 +664,20 @@ class UNet:
 
     def zero_grads(self):
         for a, b in self.live_ranges():
-            self.grads[a:b].zero_()
+            ops.fill_zero(self.grads[a:b])
 
-    def apply_gradients(self, lr0, momentum, grad_scale=1.0):
+    def apply_gradients(self, lr0, momentum, grad_scale=1.0, peer=None):
+        """tf.train.MomentumOptimizer step (+ global_step, + bf16 operand repack).  peer: a
+        dp.PeerOptimizer -- the update then also IS the gradient exchange of the data-parallel
+        ranks (each rank updates its slice from all ranks' gradients and writes everybody's
+        weights)."""
         lr = self.learning_rate(lr0)
-        for a, b in self.live_ranges():
-            ops.momentum_sgd(self.params[a:b], self.momentum[a:b], self.grads[a:b], lr, momentum,
-                             grad_scale)
+        if peer is not None:
+            peer.step(self, lr, momentum)
+        else:
+            for a, b in self.live_ranges():
+                ops.momentum_sgd(self.params[a:b], self.momentum[a:b], self.grads[a:b], lr, momentum,
+                                 grad_scale)
         self.global_step += 1
         self.pack_weights()
 

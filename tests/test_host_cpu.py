@@ -193,6 +193,35 @@ def test_shard_pairs_cover_the_training_set():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_dp_rank_slices_partition_the_live_parameters():
+    """dp.rank_slices: the slices of all ranks tile every live range of the flat parameter vector
+    exactly once, at 16-byte boundaries, whatever the world size (the fused reduce + momentum +
+    broadcast kernel of each rank works on its own slices)."""
+    from road_segmentation_unet_b200 import unet
+    from road_segmentation_unet_b200.dp import rank_slices
+    offsets, n_flat = unet.flat_layout(6, 64, True)
+    d0, d1 = offsets["conv_dilut_5/atrous_conv1/kernel"], offsets["conv_5/conv1/kernel"]
+    live = [(0, d0), (d1, n_flat)]
+    assert n_flat - (d1 - d0) >= 155776078          # live parameters of the flagship model (+ padding)
+    for world in (1, 2, 3, 4, 8):
+        cover = []
+        for r in range(world):
+            for lo, hi in rank_slices(live, r, world):
+                assert lo % 4 == 0 and hi % 4 == 0 and hi > lo
+                cover.append((lo, hi))
+        cover.sort()
+        merged = [list(cover[0])]
+        for lo, hi in cover[1:]:
+            if lo == merged[-1][1]:
+                merged[-1][1] = hi
+            else:
+                assert lo > merged[-1][1], "overlapping slices"
+                merged.append([lo, hi])
+        assert [tuple(m) for m in merged] == live
+        sizes = [sum(hi - lo for lo, hi in rank_slices(live, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 8
+
+
 def test_streaming_metrics_match_tf_metrics_semantics():
     """summary.py:141-147 / tf_aerial_images.py:428: tf.metrics.* accumulate counts over calls and
     are zeroed once per epoch; F1 = 2 / (1/recall + 1/precision); the zero entries the reference

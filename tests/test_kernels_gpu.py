@@ -618,3 +618,34 @@ def test_wgrad_cta_pair(ops, case):
     ref = w.grad.numpy().reshape(9 * cin, cout)
     assert rel_err(outs[1], ref) < 6e-3
     assert rel_err(outs[1], outs[0]) < 1e-5  # same products; only the split-K summation order differs
+
+
+def test_dp_momentum_sgd_single_rank(ops):
+    """rsu_dp_momentum_sgd with a peer table of one (world = 1: the 'peer' buffers are the local
+    ones) equals rsu_momentum_sgd on the same slice and leaves everything outside it untouched;
+    the multi-rank exchange itself is exercised by tools/test_dp.py under torchrun."""
+    import ctypes as C
+    from road_segmentation_unet_b200 import _lib
+    n = 4096 + 64
+    rs = np.random.RandomState(3)
+    w0, a0, g0 = (rs.randn(n).astype(np.float32) for _ in range(3))
+    f32 = lambda a: dev(a, torch.float32)
+    w, acc, g = f32(w0), f32(a0), f32(g0)
+    peers = _lib.DpPeers()
+    peers.world, peers.rank = 1, 0
+    peers.grads[0], peers.params[0] = g.data_ptr(), w.data_ptr()
+    lo, hi = 64, 4096
+    _lib.check(_lib.load().rsu_dp_momentum_sgd(C.byref(peers), C.c_void_p(acc.data_ptr()), lo, hi, 0.01, 0.9, 0.5,
+                                               _lib.stream_ptr()))
+    w2, a2 = f32(w0), f32(a0)
+    ops.momentum_sgd(w2[lo:hi], a2[lo:hi], f32(g0)[lo:hi], 0.01, 0.9, 0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(w, w2) and torch.equal(acc, a2)
+    assert np.array_equal(w.cpu().numpy()[:lo], w0[:lo]) and np.array_equal(w.cpu().numpy()[hi:], w0[hi:])
+    with pytest.raises(_lib.RsuError):
+        _lib.check(_lib.load().rsu_dp_momentum_sgd(C.byref(peers), C.c_void_p(acc.data_ptr()), 2, 4096, 0.01, 0.9,
+                                                   1.0, _lib.stream_ptr()))
+    z = f32(w0)
+    ops.fill_zero(z[64:128])
+    torch.cuda.synchronize()
+    assert float(z[64:128].abs().max()) == 0.0 and np.array_equal(z.cpu().numpy()[:64], w0[:64])

@@ -258,12 +258,24 @@ int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* 
  * counter-clockwise like np.rot90 / tf.image.rot90 (images.py:376-417,
  * tf_aerial_images.py:173-210).  pixel_bytes = bytes per pixel (C * sizeof element); any value. */
 int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
-                     const unsigned char* ops /* device [N] */, void* stream);
+                     const unsigned char* ops /* device [N] */,
+                     int n_in /* images in `in` (0 = N): output n transforms input n % n_in, so the
+                                 6-way ensemble of images.py:376-396 is one launch over N = 6 n_in */,
+                     void* stream);
 /* images.extract_patches (images.py:35-85): x-outer / y-inner patch order; fp32.  Only patches
  * [k_begin, k_begin + k_count) of the N*side*side patch list are written (k_count < 0 = all that
  * follow k_begin), so a prediction batch never materialises the whole patch tensor. */
 int rsu_extract_patches(const float* in, int N, int H, int W, int C, int patch, int stride,
                         long long k_begin, long long k_count, float* out, void* stream);
+/* Windows addressed by a device job table (int32 x 4 per job: source image, top row, left column,
+ * destination window index): out[dst] = in[img, y0 : y0 + win, x0 : x0 + win, :] with zeros outside
+ * the image.  The data movement of the sliding-window loop of predict() (tf_aerial_images.py:296-315)
+ * when aligned windows are evaluated together: enlarged input windows in, patch outputs out. */
+int rsu_copy_windows(const float* in, int N, int H, int W, int C, int win, long long n_jobs,
+                     const int* jobs_dev, float* out /* [*, win, win, C] */, void* stream);
+/* In place: sums[n, y, x, c] /= hit count of pixel (y, x) under side x side windows of size P at
+ * `stride` (the count_hits division of images.py:162, for partial sums reduced across ranks). */
+int rsu_divide_by_hits(float* sums, int N, int S, int C, int side, int P, int stride, void* stream);
 /* images.images_from_patches (images.py:131-164): overlap average in gather form (fp64 sums in
  * a fixed order, no atomics; 16-byte lanes when P*C and stride*C are multiples of 4 and both
  * pointers are 16-byte aligned).  `patches` points at patch k_begin of the list; with

@@ -95,7 +95,9 @@ _SIGNATURES = {
     "rsu_dp_momentum_sgd": (_i, [C.POINTER(DpPeers), _vp, _ll, _ll, _f, _f, _f, _vp]),
     "rsu_fill_zero": (_i, [_vp, _ll, _vp]),
     "rsu_mirror_pad": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "rsu_d4_transform": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rsu_d4_transform": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "rsu_copy_windows": (_i, [_vp, _i, _i, _i, _i, _i, _ll, _vp, _vp, _vp]),
+    "rsu_divide_by_hits": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rsu_extract_patches": (_i, [_vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp, _vp]),
     "rsu_overlap_average": (_i, [_vp, _i, _i, _i, _i, _i, _ll, _ll, _i, _vp, _vp]),
     "rsu_rotate_nn_crop": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _i, _i, _vp, _vp]),

@@ -125,7 +125,7 @@ __device__ __forceinline__ void d4_src_tile(int op, int S, int i0, int j0, int i
 template <typename WordT, int WORDS, int T>
 __global__ void __launch_bounds__(256)
     d4_transform_kernel(const WordT* __restrict__ in, WordT* __restrict__ out, int S,
-                        const unsigned char* __restrict__ ops) {
+                        const unsigned char* __restrict__ ops, int n_in) {
   constexpr int RW = T * WORDS;     // words per tile row
   constexpr int PITCH = RW + 1;
   constexpr int QW = (RW + 31) / 32;
@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(256)
   const int i1 = min(i0 + T - 1, S - 1), j1 = min(j0 + T - 1, S - 1);
   int si0, sj0, sh, sw;
   d4_src_tile(op, S, i0, j0, i1, j1, &si0, &sj0, &sh, &sw);
-  const WordT* __restrict__ src = in + (1LL * n * S + si0) * S * WORDS + 1LL * sj0 * WORDS;
+  // (output image n reads input image n % n_in: the 6-way ensemble transforms every input six times)
+  const WordT* __restrict__ src = in + (1LL * (n % n_in) * S + si0) * S * WORDS + 1LL * sj0 * WORDS;
   WordT* __restrict__ dst = out + (1LL * n * S + i0) * S * WORDS + 1LL * j0 * WORDS;
   const int tx = threadIdx.x, ty = threadIdx.y;
   WordT v[QR][QW];
@@ -174,7 +175,8 @@ __global__ void __launch_bounds__(256)
 // any pixel size (fp64 images travel as 2 x 32-bit words per element): run-time word count
 template <typename WordT>
 __global__ void d4_transform_generic_kernel(const WordT* __restrict__ in, WordT* __restrict__ out,
-                                            int S, int words, const unsigned char* __restrict__ ops) {
+                                            int S, int words, const unsigned char* __restrict__ ops,
+                                            int n_in) {
   extern __shared__ uint8_t tile_raw[];  // [32][32*words + 1] words
   WordT* tile = reinterpret_cast<WordT*>(tile_raw);
   const int n = blockIdx.z;
@@ -184,7 +186,7 @@ __global__ void d4_transform_generic_kernel(const WordT* __restrict__ in, WordT*
   int si0, sj0, sh, sw;
   d4_src_tile(op, S, i0, j0, i1, j1, &si0, &sj0, &sh, &sw);
   const int pitch = 32 * words + 1;
-  const WordT* src = in + 1LL * n * S * S * words;
+  const WordT* src = in + 1LL * (n % n_in) * S * S * words;
   WordT* dst = out + 1LL * n * S * S * words;
   for (int r = threadIdx.y; r < sh; r += blockDim.y)
     for (int w = threadIdx.x; w < sw * words; w += blockDim.x)
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(256)
                       unsigned char* __restrict__ labels) {
   extern __shared__ double col_sum[];                                     // [S] then labels [cells]
   unsigned char* label_s = reinterpret_cast<unsigned char*>(col_sum + S);
-  const int cy = blockIdx.x, n = blockIdx.y;
+  const int cy = blockIdx.y, n = blockIdx.x;
   const int y0 = cy * patch, h = min(patch, S - y0);
   const T* __restrict__ src = masks + (1LL * n * S + y0) * S;
   for (int x = threadIdx.x; x < S; x += blockDim.x) {
@@ -527,11 +529,109 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Windows of a batch of images addressed by a device job table: job j copies the win x win window
+// of image jobs[j].x whose top-left pixel is (jobs[j].y, jobs[j].z) -- pixels outside the image
+// read as zero -- into window jobs[j].w of `out`.  One block per (job, window row).  Serves both
+// directions of the shared-window prediction (tf_aerial_images.shared_window_plan): cutting the
+// enlarged input windows out of the mirror-padded images, and cutting the patch outputs out of the
+// enlarged probability maps straight into their slots of the patch list.
+template <int VEC>
+__global__ void __launch_bounds__(128)
+    copy_windows_kernel(const float* __restrict__ in, int H, int W, int C, int win,
+                        const int4* __restrict__ jobs, float* __restrict__ out) {
+  const int j = blockIdx.x / win, r = blockIdx.x - j * win;
+  const int4 job = __ldg(jobs + j);
+  const int y = job.y + r;
+  const int n_el = win * C;
+  float* __restrict__ dst = out + (1LL * job.w * win + r) * n_el;
+  const bool row_in = y >= 0 && y < H;
+  const int x_lo = max(0, -job.z), x_hi = min(win, W - job.z);  // window columns inside the image
+  const int e_lo = row_in ? x_lo * C : n_el, e_hi = row_in ? max(x_hi * C, e_lo) : n_el;
+  const float* __restrict__ src = in + ((1LL * job.x * H + (row_in ? y : 0)) * W + job.z) * C;
+  if (VEC && e_lo == 0 && e_hi == n_el && aligned16(src)) {
+    constexpr int U = 4;
+    const int n4 = n_el >> 2;
+    for (int g0 = threadIdx.x; g0 < n4; g0 += blockDim.x * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = g0 + u * blockDim.x;
+        if (g < n4) v[u] = __ldg(reinterpret_cast<const float4*>(src) + g);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = g0 + u * blockDim.x;
+        if (g < n4) reinterpret_cast<float4*>(dst)[g] = v[u];
+      }
+    }
+  } else {
+    constexpr int U = 8;
+    for (int e0 = threadIdx.x; e0 < n_el; e0 += blockDim.x * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < n_el) v[u] = (e >= e_lo && e < e_hi) ? __ldg(src + e) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < n_el) dst[e] = v[u];
+      }
+    }
+  }
+}
+
+// sums[n, y, x, c] /= number of sliding windows covering pixel (y, x): the analytic hit count of
+// images_from_patches (images.py:154-162) for side x side patches of size P at `stride`.
+__global__ void __launch_bounds__(256)
+    divide_by_hits_kernel(float* __restrict__ sums, int S, int C, int side, int P, int stride,
+                          long long total) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const long long px = i / C;
+    const int x = static_cast<int>(px % S), y = static_cast<int>((px / S) % S);
+    const int ky_lo = (y - P + 1 <= 0) ? 0 : (y - P + stride) / stride, ky_hi = min(y / stride, side - 1);
+    const int kx_lo = (x - P + 1 <= 0) ? 0 : (x - P + stride) / stride, kx_hi = min(x / stride, side - 1);
+    const int cnt = (ky_hi - ky_lo + 1) * (kx_hi - kx_lo + 1);
+    sums[i] = static_cast<float>(static_cast<double>(sums[i]) / static_cast<double>(cnt));
+  }
+}
+
 }  // namespace rsu
 
 using namespace rsu;
 
 extern "C" {
+
+int rsu_copy_windows(const float* in, int N, int H, int W, int C, int win, long long n_jobs,
+                     const int* jobs_dev, float* out, void* stream) {
+  if (N < 1 || H < 1 || W < 1 || C < 1 || win < 1 || n_jobs < 0)
+    return set_error(RSU_EINVAL, "copy_windows: shape");
+  if (n_jobs == 0) return RSU_OK;
+  if (reinterpret_cast<uintptr_t>(jobs_dev) & 15) return set_error(RSU_EALIGN, "copy_windows: job table");
+  const long long rows = n_jobs * win;
+  if (rows > 0x7fffffffLL || 1LL * win * C > 0x7fffffffLL)
+    return set_error(RSU_EINVAL, "copy_windows: more than 2^31 window rows");
+  const bool vec = (win * C) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int4* jobs = reinterpret_cast<const int4*>(jobs_dev);
+  if (vec)
+    copy_windows_kernel<1><<<static_cast<unsigned>(rows), 128, 0, (cudaStream_t)stream>>>(in, H, W, C, win, jobs, out);
+  else
+    copy_windows_kernel<0><<<static_cast<unsigned>(rows), 128, 0, (cudaStream_t)stream>>>(in, H, W, C, win, jobs, out);
+  return check_launch("copy_windows");
+}
+
+int rsu_divide_by_hits(float* sums, int N, int S, int C, int side, int P, int stride, void* stream) {
+  if (N < 1 || S < 1 || C < 1 || side < 1 || P < 1 || stride < 1 || S != (side - 1) * stride + P)
+    return set_error(RSU_EINVAL, "divide_by_hits: shape (S must be (side - 1) * stride + P)");
+  const long long total = 1LL * N * S * S * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  divide_by_hits_kernel<<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(sums, S, C, side, P,
+                                                                                        stride, total);
+  return check_launch("divide_by_hits");
+}
 
 int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* out, void* stream) {
   if (N < 1 || H < 1 || W < 1 || C < 1 || pad < 0) return set_error(RSU_EINVAL, "mirror_pad: shape");
@@ -556,9 +656,10 @@ int rsu_mirror_pad(const float* in, int N, int H, int W, int C, int pad, float* 
 }
 
 int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
-                     const unsigned char* ops, void* stream) {
-  if (N < 1 || S < 1 || pixel_bytes < 1)
+                     const unsigned char* ops, int n_in, void* stream) {
+  if (N < 1 || S < 1 || pixel_bytes < 1 || n_in < 0)
     return set_error(RSU_EINVAL, "d4_transform: bad shape N=%d S=%d pixel_bytes=%d", N, S, pixel_bytes);
+  if (n_in == 0) n_in = N;
   if (in == out) return set_error(RSU_EINVAL, "d4_transform: in-place not supported");
   if (N > 65535) return set_error(RSU_EINVAL, "d4_transform: N > 65535");
   cudaStream_t st = (cudaStream_t)stream;
@@ -568,24 +669,24 @@ int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
                      (reinterpret_cast<uintptr_t>(out) & 3) == 0;
   if (word4 && pixel_bytes == 12) {  // RGB fp32
     d4_transform_kernel<uint32_t, 3, 32><<<g32, block, 0, st>>>(
-        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops);
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops, n_in);
   } else if (word4 && pixel_bytes == 4) {  // fp32 masks
     d4_transform_kernel<uint32_t, 1, 64><<<g64, block, 0, st>>>(
-        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops);
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops, n_in);
   } else if (pixel_bytes == 1) {  // uint8 label masks
     d4_transform_kernel<uint8_t, 1, 64><<<g64, block, 0, st>>>(
-        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, ops);
+        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, ops, n_in);
   } else if (word4) {
     const int words = pixel_bytes / 4;
     const size_t smem = 32 * (32 * words + 1) * sizeof(uint32_t);
     if (smem > 48 * 1024) return set_error(RSU_EINVAL, "d4_transform: pixel too large");
     d4_transform_generic_kernel<uint32_t><<<g32, block, smem, st>>>(
-        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, words, ops);
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, words, ops, n_in);
   } else {  // byte-granular pixels
     const size_t smem = 32 * (32 * pixel_bytes + 1);
     if (smem > 48 * 1024) return set_error(RSU_EINVAL, "d4_transform: pixel too large");
     d4_transform_generic_kernel<uint8_t><<<g32, block, smem, st>>>(
-        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, pixel_bytes, ops);
+        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, pixel_bytes, ops, n_in);
   }
   return check_launch("d4_transform");
 }
@@ -682,10 +783,10 @@ int rsu_patch_vote(const void* masks, int elem_bytes, int N, int S, int patch, i
     return set_error(RSU_EINVAL, "patch_vote: shape / rule");
   if (elem_bytes != 4 && elem_bytes != 8) return set_error(RSU_EINVAL, "patch_vote: fp32 or fp64 masks");
   const int g = (S + patch - 1) / patch;
-  if (N > 65535) return set_error(RSU_EINVAL, "patch_vote: N > 65535");
+  if (g > 65535) return set_error(RSU_EINVAL, "patch_vote: more than 65535 cells per side");
   const size_t smem = sizeof(double) * S + ((g + 7) / 8) * 8;
   if (smem > 48 * 1024) return set_error(RSU_EINVAL, "patch_vote: mask side %d too large", S);
-  const dim3 grid(g, N);
+  const dim3 grid(N, g);  // (masks in grid.x: any number of them)
   const cudaStream_t st = (cudaStream_t)stream;
   if (elem_bytes == 4)
     patch_vote_kernel<float><<<grid, 256, smem, st>>>(static_cast<const float*>(masks), S, patch, g, rule,

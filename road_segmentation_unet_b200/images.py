@@ -59,13 +59,17 @@ def mirror_border_dev(x, n):
     return out
 
 
-def d4_transform_dev(x, ops_u8):
-    """Per-image dihedral transform: out[i] = rot90(flipud(x[i]) if op&4 else x[i], k=op&3)."""
-    N, S = x.shape[0], x.shape[1]
+def d4_transform_dev(x, ops_u8, repeat=1):
+    """Per-image dihedral transform: out[i] = rot90(flipud(x[j]) if op&4 else x[j], k=op&3) with
+    j = i % len(x); `repeat` > 1 transforms every input image that many times (ops_u8 has
+    repeat * len(x) entries) without materialising the repeated input."""
+    n_in, S = x.shape[0], x.shape[1]
     assert x.shape[2] == S, "square images required"
     pixel_bytes = x.element_size() * (x.shape[3] if x.dim() == 4 else 1)
-    out = torch.empty_like(x)
-    call("rsu_d4_transform", _ptr(x), _ptr(out), N, S, pixel_bytes, _ptr(ops_u8))
+    N = n_in * repeat
+    assert ops_u8.numel() == N
+    out = torch.empty((N,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    call("rsu_d4_transform", _ptr(x), _ptr(out), N, S, pixel_bytes, _ptr(ops_u8), n_in)
     return out
 
 
@@ -74,9 +78,8 @@ ENSEMBLE_OPS = (0, 4 | 2, 4, 1, 2, 3)  # orig, fliplr, flipud, rot90 k=1,2,3  (i
 
 def image_augmentation_ensemble_dev(x):
     n = x.shape[0]
-    rep = x.repeat(6, 1, 1, 1)
     ops_t = torch.tensor([op for op in ENSEMBLE_OPS for _ in range(n)], dtype=torch.uint8, device=x.device)
-    return d4_transform_dev(rep, ops_t)
+    return d4_transform_dev(x.contiguous(), ops_t, repeat=6)  # variant-major, one launch
 
 
 def extract_patches_dev(x, patch_size, stride, k_begin=0, k_count=-1, out=None):
@@ -89,6 +92,23 @@ def extract_patches_dev(x, patch_size, stride, k_begin=0, k_count=-1, out=None):
     call("rsu_extract_patches", _ptr(x), N, H, W, Cc, int(patch_size), int(stride), int(k_begin),
          int(cnt), _ptr(out))
     return out
+
+
+def copy_windows_dev(x, win, jobs, out):
+    """out[dst] = x[img, y0:y0+win, x0:x0+win, :] (zeros outside the image) for every row
+    (img, y0, x0, dst) of the int32 CUDA job table `jobs` [n, 4]  (rsu_copy_windows)."""
+    N, H, W, Cc = x.shape
+    assert jobs.dtype == torch.int32 and jobs.dim() == 2 and jobs.shape[1] == 4 and jobs.is_contiguous()
+    assert out.shape[1:] == (win, win, Cc) and out.is_contiguous() and x.is_contiguous()
+    call("rsu_copy_windows", _ptr(x), N, H, W, Cc, int(win), int(jobs.shape[0]), _ptr(jobs), _ptr(out))
+    return out
+
+
+def divide_by_hits_dev(sums, side, patch_size, stride):
+    """In place: overlap-add partial sums [N,S,S,C] -> averages (analytic hit counts)."""
+    N, S, _, Cc = sums.shape
+    call("rsu_divide_by_hits", _ptr(sums), N, S, Cc, int(side), int(patch_size), int(stride))
+    return sums
 
 
 def images_from_patches_dev(patches, num_images, side, stride, k_begin=0, k_count=-1, normalize=True):

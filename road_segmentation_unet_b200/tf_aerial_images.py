@@ -600,15 +600,6 @@ class ConvolutionalModel:
         print("Prediction Done")
         return masks.cpu().numpy().astype(np.float64)
 
-    def _overlap_counts(self, out_side, side):
-        """hit count of every mask pixel (analytic; used to normalise all-reduced partial sums)"""
-        P, stride = self._options.patch_size, self._options.stride
-        pos = np.arange(out_side)
-        lo = np.where(pos - P + 1 <= 0, 0, (pos - P + stride) // stride)
-        hi = np.minimum(pos // stride, side - 1)
-        cnt1 = (hi - lo + 1).astype(np.float32)
-        return torch.from_numpy(np.outer(cnt1, cnt1)).cuda()[None, :, :, None]
-
     def _predict_windows(self, x, num_images, side):
         """every sliding window is its own forward pass (the reference's loop, :296-315); ranks
         take contiguous slices of the patch list"""
@@ -635,7 +626,7 @@ class ConvolutionalModel:
         part = images.images_from_patches_dev(preds, num_images, side, opts.stride, k0, k1 - k0,
                                               normalize=False)
         self._dist.dist.all_reduce(part)  # the single exchange of a sharded prediction
-        return part / self._overlap_counts(part.shape[1], side)
+        return images.divide_by_hits_dev(part, side, P, opts.stride)
 
     def _shared_net(self, big_input, big_batch):
         """Forward-only engine for enlarged windows.  It aliases the training engine's master and
@@ -662,17 +653,12 @@ class ConvolutionalModel:
         world, rank = self._dist.world, self._dist.rank
         S, P, B, stride = self.input_size, opts.patch_size, opts.batch_size, opts.stride
         n, q, wins = plan
-        # zero-extended copy of the padded images: every enlarged-window origin becomes a regular
-        # patch position of extract_patches (content beyond the image only reaches outputs that
-        # are never used)
-        H = x.shape[1]
-        Hz = max(H, stride * max(w[0] for w in wins) + S + q * (n - 1))
-        xz = torch.zeros(num_images, Hz, Hz, NUM_CHANNELS, dtype=torch.float32, device="cuda")
-        xz[:, :H, :H].copy_(x)
         by_size = shared_window_jobs(num_images, wins, rank, world)
         num_patches = num_images * side * side
-        alloc = torch.empty if world == 1 else torch.zeros
-        preds = alloc(num_patches, P, P, 1, dtype=torch.float32, device="cuda")
+        preds = torch.empty(num_patches, P, P, 1, dtype=torch.float32, device="cuda")
+        if world > 1:  # foreign patches stay zero in this rank's partial sums
+            from . import ops as _ops
+            _ops.fill_zero(preds)
         for m, group in sorted(by_size.items()):
             win_in, win_out = S + q * (m - 1), P + q * (m - 1)
             if m == 1:
@@ -684,28 +670,36 @@ class ConvolutionalModel:
                 win_b = -(-len(group) // -(-len(group) // win_b))
                 net = self._shared_net(win_in, win_b)
                 win_b = net.B
-            assert net.P == win_out and (Hz - win_in) % stride == 0
-            side_z = (Hz - win_in) // stride + 1
-            batch = torch.empty(win_b, win_in, win_in, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+            assert net.P == win_out
+            # device job tables of the whole group, uploaded once: (image, top row, left column,
+            # destination) of every enlarged input window -- pixels beyond the padded image read
+            # as zero and only reach outputs that are never used -- and of every patch output that
+            # is cut out of the enlarged probability maps into its slot of the patch list
+            t_in, t_out, out_ofs = [], [], [0]
+            for jj, (img, wx, wy) in enumerate(group):
+                slot = jj % win_b
+                t_in.append((img, stride * wy[0], stride * wx[0], slot))
+                for mx, kx in enumerate(wx):
+                    for my, ky in enumerate(wy):
+                        t_out.append((slot, my * q, mx * q, (img * side + kx) * side + ky))
+                out_ofs.append(len(t_out))
+            jobs_in = torch.tensor(t_in, dtype=torch.int32).cuda()
+            jobs_out = torch.tensor(t_out, dtype=torch.int32).cuda()
+            batch = self.__dict__.setdefault("_window_batches", {}).get((win_b, win_in))
+            if batch is None:
+                batch = torch.empty(win_b, win_in, win_in, NUM_CHANNELS, dtype=torch.float32, device="cuda")
+                self._window_batches[(win_b, win_in)] = batch
             for j in range(0, len(group), win_b):
-                chunk = group[j:j + win_b]
-                src, dst = [], []
-                for i, (img, wx, wy) in enumerate(chunk):
-                    images.extract_patches_dev(xz, win_in, stride, (img * side_z + wx[0]) * side_z + wy[0],
-                                               1, out=batch[i:i + 1])
-                    for mx, kx in enumerate(wx):
-                        for my, ky in enumerate(wy):
-                            src.append((i * m + mx) * m + my)
-                            dst.append((img * side + kx) * side + ky)
+                cnt = min(win_b, len(group) - j)
+                images.copy_windows_dev(x, win_in, jobs_in[j:j + cnt], batch)
                 net.forward(batch, keep=1.0)
-                cut = images.extract_patches_dev(net.probs.view(win_b, win_out, win_out, 1), P, q)
-                preds.index_copy_(0, torch.tensor(dst, device="cuda"),
-                                  cut.index_select(0, torch.tensor(src, device="cuda")))
+                images.copy_windows_dev(net.probs.view(net.B, win_out, win_out, 1), P,
+                                        jobs_out[out_ofs[j]:out_ofs[j + cnt]], preds)
         if world == 1:
             return images.images_from_patches_dev(preds, num_images, side, stride)
         part = images.images_from_patches_dev(preds, num_images, side, stride, normalize=False)
         self._dist.dist.all_reduce(part)  # the single exchange of a sharded prediction
-        return part / self._overlap_counts(part.shape[1], side)
+        return images.divide_by_hits_dev(part, side, P, stride)
 
     def predict_batchwise(self, imgs, pred_batch_size):
         masks = []

@@ -204,3 +204,38 @@ def test_scoring_rules(images, tmp_path):
     lt = images.patch_labels(tm, 16, rule=images.RULE_VOTE)
     assert lp.shape == (3, 38, 38)
     assert abs(images.patch_scores(lp, lt)[3] - IO.patch_f1(pm, tm)) < 1e-12
+
+
+def test_copy_windows_and_divide_by_hits():
+    """rsu_copy_windows (job-table window copies with zero fill outside the image: the data movement
+    of the shared-window prediction) and rsu_divide_by_hits (analytic count_hits division of
+    images.py:154-162) against NumPy, bit-exact / 1e-7."""
+    from road_segmentation_unet_b200 import images
+    rs = np.random.RandomState(9)
+    for C_, win, H in ((3, 40, 52), (1, 17, 30), (3, 36, 33)):
+        x = rs.rand(3, H, H, C_).astype(np.float32)
+        jobs = [(0, 0, 0, 2), (1, 12, 8, 0), (2, H - win + 5, -3, 1), (1, -4, H - 10, 3)]
+        out = torch.full((4, win, win, C_), -7.0, dtype=torch.float32, device="cuda")
+        images.copy_windows_dev(torch.tensor(x).cuda(), win, torch.tensor(jobs, dtype=torch.int32).cuda(), out)
+        got = out.cpu().numpy()
+        for img, y0, x0, dst in jobs:
+            want = np.zeros((win, win, C_), np.float32)
+            ys, xs = np.arange(y0, y0 + win), np.arange(x0, x0 + win)
+            vy, vx = (ys >= 0) & (ys < H), (xs >= 0) & (xs < H)
+            want[np.ix_(vy, vx)] = x[img][np.ix_(ys[vy], xs[vx])]
+            assert np.array_equal(got[dst], want), (C_, win, H, dst)
+    # overlap-add partial sums / hit counts == the reference's average
+    side, P, stride = 4, 20, 8
+    patches = rs.rand(2, side * side, P, P, 1)
+    ref = IO.images_from_patches(patches, stride=stride)
+    p = torch.tensor(patches.reshape(-1, P, P, 1), dtype=torch.float32).cuda()
+    sums = images.images_from_patches_dev(p, 2, side, stride, normalize=False)
+    avg = images.divide_by_hits_dev(sums, side, P, stride).cpu().numpy()
+    assert np.abs(avg - ref).max() < 1e-6
+    # d4 with repeated inputs == the ensemble of the reference (variant-major), one launch
+    x = rs.rand(2, 12, 12, 3).astype(np.float32)
+    ens = images.image_augmentation_ensemble_dev(torch.tensor(x).cuda()).cpu().numpy()
+    assert np.array_equal(ens, IO.image_augmentation_ensemble(x).astype(np.float32))
+    # any number of patches through the vote kernel (masks ride in grid.x)
+    many = (rs.rand(70000, 4, 4) > 0.6).astype(np.float32)
+    assert np.array_equal(images.labels_for_patches(many), IO.labels_for_patches(many))

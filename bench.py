@@ -247,6 +247,122 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------ BASELINE.json configs[4]
+def activation_bytes(L, root, dilated, P, training=True):
+    """bf16 bytes of the engine's activation (+ gradient) buffers per patch: what bounds the
+    per-GPU micro-batch of the large-tile configurations."""
+    from road_segmentation_unet_b200 import unet
+    S = unet.input_size_needed(P, L)
+    f = [root * 2 ** i for i in range(L)]
+    in_size, s = [], S
+    for i in range(L):
+        in_size.append(s)
+        s = (s - 4) // 2
+    up, net = [], in_size[L - 1] - 4
+    for j in range(L - 1):
+        up.append(2 * net)
+        net = 2 * net - 4
+    fwd = bwd = 0
+    for i in range(L):
+        s = in_size[i]
+        fwd += ((s - 2) ** 2 + (s - 4) ** 2 + (((s - 4) // 2) ** 2 if i < L - 1 else 0)) * f[i]
+        bwd += ((s - 2) ** 2 + (s - 4) ** 2) * f[i] + (s * s * f[i - 1] if i > 0 else 0)
+        if dilated and i < L - 1:
+            t = up[L - 2 - i]
+            fwd += ((t + 4) ** 2 + t * t) * f[i]
+            bwd += (t + 4) ** 2 * f[i]
+    for j in range(L - 1):
+        fo, t = f[L - 2 - j], up[j]
+        fwd += (t * t + (t - 2) ** 2 + (t - 4) ** 2) * fo
+        bwd += (t * t * (3 if dilated else 2) + (t - 2) ** 2 + (t - 4) ** 2) * fo
+    return 2 * (fwd + (bwd if training else 0)) + S * S * 3 * 4
+
+
+def run_large_tiles(args, torch, dist, tfa, unet, world, rank, barrier):
+    """BASELINE.json configs[4]: root_size 64 / 128 U-Net (L=6, dilated) on 1024^2 / 2048^2 tiles,
+    global batch 64 over 8 GPUs = 8 patches per GPU, bf16 train + predict.  1024 and 2048 are not
+    valid patch sizes (unet.input_size_needed: P must be a multiple of 32 plus 4), so
+      train:   tiles as patches, P = 1028 (1404^2 inputs) and P = 2052 (2428^2 inputs); 8 patches per
+               GPU and optimizer step, as micro-batches that fit in HBM (gradient accumulation);
+      predict: tiles as images, one synthetic 1024^2 image at stride 12 and one 2048^2 image at
+               stride 20 per call, 6-way ensemble, 388^2 windows, work sharded over the ranks."""
+    out = {"train": [], "predict": []}
+    peak, peak_sus, _, _ = measured_peaks()
+    free_b = torch.cuda.mem_get_info()[0]
+    for root, P in ((64, 1028), (128, 1028), (64, 2052), (128, 2052)):
+        per_patch = activation_bytes(6, root, True, P)
+        n_params = sum(int(np.prod(sh)) for sh in unet.variable_shapes(6, root, True).values())
+        budget = int(0.8 * (free_b - n_params * 4 * 5 - (6 << 30)))
+        micro = max(1, min(8, int(budget // per_patch)))
+        while 8 % micro:
+            micro -= 1
+        opts = tfa.Options()
+        opts.batch_size, opts.num_layers, opts.root_size, opts.dilated_layers = micro, 6, root, True
+        opts.patch_size, opts.dropout, opts.lr, opts.momentum = P, 1.0, 0.01, 0.9
+        model = tfa.ConvolutionalModel(opts, None)
+        net, S = model.net, model.input_size
+        g = torch.Generator(device="cuda").manual_seed(2017 + rank)
+        mb = [(torch.rand(micro, S, S, 3, device="cuda", generator=g),
+               (torch.rand(micro, P, P, device="cuda", generator=g) < 0.3).to(torch.uint8))
+              for _ in range(8 // micro)]
+        finish = (lambda: model._reducer.finish()) if model._reducer is not None else None
+
+        def step():
+            net.accumulate_step(mb, opts.lr, opts.momentum, peer=model._peer, finish=finish)
+
+        step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        K = 3
+        for _ in range(K):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / K
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        f_alg = 3 * sum(unet.plan_flops(6, root, True, P).values())
+        pps = world * 8 / (ms / 1e3)
+        out["train"].append({"root_size": root, "patch_size": P, "input_size": S, "global_batch": 8 * world,
+                             "micro_batch": micro, "ms_per_step": ms, "patches_per_s": pps,
+                             "tflops_per_gpu": pps / world * f_alg / 1e12,
+                             "frac_of_sustained_peak": pps / world * f_alg / 1e12 / peak_sus,
+                             "loss": float(net.loss.item())})
+        del model, net, mb
+        torch.cuda.empty_cache()
+    # predict: the flagship model (388^2 windows) over large images
+    for root in (64, 128):
+        opts = tfa.Options()
+        opts.batch_size, opts.num_layers, opts.root_size, opts.dilated_layers = 32 if root == 64 else 16, 6, root, True
+        opts.patch_size, opts.dropout, opts.ensemble_prediction = 388, 1.0, True
+        model = tfa.ConvolutionalModel(opts, None)
+        for size, stride in ((1024, 12), (2048, 20)):
+            opts.stride = stride
+            img = np.random.RandomState(2017).rand(1, size, size, 3).astype(np.float32)
+            with contextlib.redirect_stdout(io.StringIO()):
+                model.predict(img)  # warm-up: allocates the enlarged-window engines of this plan
+                barrier()
+                t0 = time.perf_counter()
+                mask = model.predict(img)
+                torch.cuda.synchronize()
+                sec = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([sec], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec = float(t.item())
+            side = (size + 376 - 764) // stride + 1
+            out["predict"].append({"root_size": root, "image": size, "stride": stride, "windows": 6 * side * side,
+                                   "seconds": sec, "mpix_per_s": size * size / 1e6 / sec,
+                                   "window_equivalents_per_s": 6 * side * side / sec,
+                                   "mask_mean": float(mask.mean())})
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -313,6 +429,20 @@ def run_gpu(args):
         ms = float(t.item())
     ms_per_step = ms / K
     value = world * B * K / (ms / 1e3)
+
+    if args.large_tiles:  # BASELINE.json configs[4] only (its own line; not the headline config)
+        del x, lab
+        model._net = None
+        del model, net
+        torch.cuda.empty_cache()
+        res = run_large_tiles(args, torch, dist, tfa, unet, world, rank, barrier)
+        if rank == 0:
+            print(json.dumps({"metric": "large-tile sweep (BASELINE.json configs[4])", "n_gpus": world,
+                              "headline_value": value, "large_tiles": res}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     if args.quick:  # profiling runs (ncu): only the device-timed region
         if rank == 0:
@@ -572,6 +702,9 @@ def main():
     ap.add_argument("--no-predict", action="store_true", help="skip the sliding-window prediction leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernel table")
     ap.add_argument("--predict-images", type=int, default=1, help="604^2 images in the prediction leg")
+    ap.add_argument("--large-tiles", action="store_true",
+                    help="run the BASELINE.json configs[4] sweep (P = 1028 / 2052, root 64 / 128) instead of "
+                         "the prediction / roofline / CPU legs")
     ap.add_argument("--dump-layers", default="", help="write the per-layer tcgen05 kernel timing table here")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON record: everything else that libraries write to

@@ -582,7 +582,7 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ v, long long 
 //   dl1 = (P(road) - label) / count = -dl0,  dZ = dl1 * (w1 - w0),  dW[:,0] = -dW[:,1]
 // -- which halves the arithmetic of this instruction-bound (not yet HBM-bound) kernel.  The
 // separate logits l0, l1 are only evaluated when the caller asks for them (LOGITS).
-template <int LP, bool LOGITS>
+template <int LP, bool LOGITS, int U_ = 4>
 __global__ void __launch_bounds__(256, 3)
     head_kernel(const uint4* __restrict__ act, long long pixels, const float* __restrict__ w,
                 const float* __restrict__ b, const unsigned char* __restrict__ labels,
@@ -609,7 +609,8 @@ __global__ void __launch_bounds__(256, 3)
   const long long n_warps = (1LL * gridDim.x * blockDim.x) >> 5;
   // U pixel groups per iteration: all activation (and label) loads are issued before the first
   // dependent instruction
-  constexpr int U = 4;
+  // (U_ = 8 for prediction: no gradient state in registers, so twice the loads fit in flight)
+  constexpr int U = U_;
   for (long long p0 = warp_global * (PPW * U); p0 < pixels; p0 += n_warps * (PPW * U)) {
     uint4 raw[U];
     int lab[U];
@@ -962,6 +963,10 @@ int rsu_head(const void* act, int N, int H, int W, int C, const float* w, const 
   do {                                                                                       \
     if (logits)                                                                              \
       head_kernel<LP, true><<<grid, threads, 0, (cudaStream_t)stream>>>(                     \
+          static_cast<const uint4*>(act), pixels, w, b, labels, probs, logits, loss,        \
+          static_cast<uint4*>(dZ), dW, db, inv_count);                                      \
+    else if (labels == nullptr)                                                              \
+      head_kernel<LP, false, 8><<<grid, threads, 0, (cudaStream_t)stream>>>(                 \
           static_cast<const uint4*>(act), pixels, w, b, labels, probs, logits, loss,        \
           static_cast<uint4*>(dZ), dW, db, inv_count);                                      \
     else                                                                                     \

@@ -172,6 +172,86 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The same transform with VB-byte global accesses (16 for fp32 pixels, 4 for uint8 label masks):
+// the element-wise kernel above issues ~25 instructions per 4 bytes moved and is bound by
+// instruction issue at half of the HBM bandwidth.  Needs S * pixel bytes to be a multiple of VB
+// (then every tile row of the source and of the destination starts VB-aligned) and VB-aligned
+// base pointers.  The source tile is read row-wise into shared memory as vectors; every thread
+// then gathers the words of one destination vector through the affine map
+//   (source row, source column) - tile origin = (ai, aj) * r + (bi, bj) * j + (ci, cj)
+// of the dihedral element, whose coefficients are computed once per block.
+template <typename WordT, int WORDS, int T, typename VecT>
+__global__ void __launch_bounds__(256)
+    d4_transform_vec_kernel(const WordT* __restrict__ in, WordT* __restrict__ out, int S,
+                            const unsigned char* __restrict__ ops, int n_in) {
+  constexpr int VW = sizeof(VecT) / sizeof(WordT);  // words per vector
+  constexpr int RW = T * WORDS;                     // words per full tile row
+  constexpr int RV = RW / VW;                       // vectors per full tile row
+  constexpr int PITCH = RW + (sizeof(WordT) == 4 ? 1 : 4);
+  constexpr int Q = (T * RV + 255) / 256;
+  static_assert(RW % VW == 0, "tile rows must be whole vectors");
+  __shared__ WordT tile[T * PITCH];
+  const int n = blockIdx.z;
+  const int op = ops[n];
+  const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+  const int i1 = min(i0 + T - 1, S - 1), j1 = min(j0 + T - 1, S - 1);
+  int si0, sj0, sh, sw;
+  d4_src_tile(op, S, i0, j0, i1, j1, &si0, &sj0, &sh, &sw);
+  const WordT* __restrict__ src = in + (1LL * (n % n_in) * S + si0) * S * WORDS + 1LL * sj0 * WORDS;
+  WordT* __restrict__ dst = out + (1LL * n * S + i0) * S * WORDS + 1LL * j0 * WORDS;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const long long row_words = 1LL * S * WORDS;
+  // ---- source tile -> shared memory, row-wise, Q vectors per thread in flight
+  const int src_rv = sw * WORDS / VW;  // vectors per source tile row (== RV for interior tiles)
+  VecT v[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int idx = tid + q * 256;
+    const int rr = src_rv == RV ? idx / RV : idx / src_rv;
+    const int c = idx - rr * src_rv;
+    if (rr < sh) v[q] = __ldg(reinterpret_cast<const VecT*>(src + rr * row_words) + c);
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int idx = tid + q * 256;
+    const int rr = src_rv == RV ? idx / RV : idx / src_rv;
+    const int c = idx - rr * src_rv;
+    if (rr < sh) {
+      const WordT* w = reinterpret_cast<const WordT*>(&v[q]);
+#pragma unroll
+      for (int k = 0; k < VW; ++k) tile[rr * PITCH + c * VW + k] = w[k];
+    }
+  }
+  __syncthreads();
+  // ---- affine map of the block: shared-memory word index of destination (r, j, e)
+  int o_i, o_j, r_i, r_j, c_i, c_j;
+  d4_src(op, S, i0, j0, &o_i, &o_j);
+  d4_src(op, S, i0 + 1, j0, &r_i, &r_j);
+  d4_src(op, S, i0, j0 + 1, &c_i, &c_j);
+  const int step_r = (r_i - o_i) * PITCH + (r_j - o_j) * WORDS;
+  const int step_j = (c_i - o_i) * PITCH + (c_j - o_j) * WORDS;
+  const int base = (o_i - si0) * PITCH + (o_j - sj0) * WORDS;
+  const int th = i1 - i0 + 1, tw = j1 - j0 + 1;
+  const int dst_rv = tw * WORDS / VW;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int idx = tid + q * 256;
+    const int rr = dst_rv == RV ? idx / RV : idx / dst_rv;
+    const int c = idx - rr * dst_rv;
+    if (rr < th) {
+      VecT o;
+      WordT* w = reinterpret_cast<WordT*>(&o);
+#pragma unroll
+      for (int k = 0; k < VW; ++k) {
+        const int word = c * VW + k;
+        const int j = word / WORDS, e = word - j * WORDS;
+        w[k] = tile[base + rr * step_r + j * step_j + e];
+      }
+      reinterpret_cast<VecT*>(dst + rr * row_words)[c] = o;
+    }
+  }
+}
+
 // any pixel size (fp64 images travel as 2 x 32-bit words per element): run-time word count
 template <typename WordT>
 __global__ void d4_transform_generic_kernel(const WordT* __restrict__ in, WordT* __restrict__ out,
@@ -529,6 +609,58 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same with 16-byte accesses (S a multiple of 4, 16-byte-aligned buffers): one float4 per thread
+// and variant on the way in (six independent loads in flight), one float4 per thread on the way
+// out; the six gathers go through per-variant affine maps computed once per block.
+__global__ void __launch_bounds__(256)
+    ensemble_invert_vec_kernel(const float* __restrict__ masks, int N, int S, float* __restrict__ out) {
+  constexpr int T = 32, PITCH = 33;
+  __shared__ float t[6][T * PITCH];
+  const int n = blockIdx.z;
+  const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+  const int i1 = min(i0 + T - 1, S - 1), j1 = min(j0 + T - 1, S - 1);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int rr = tid >> 3, c4 = (tid & 7) << 2;  // row of the tile, first of four columns
+  const int inv_ops[6] = {0, 4 | 2, 4, 3, 2, 1};
+  const long long img = 1LL * S * S;
+  float4 v[6];
+  int base[6], step_r[6], step_j[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    int si0, sj0, sh, sw;
+    d4_src_tile(inv_ops[k], S, i0, j0, i1, j1, &si0, &sj0, &sh, &sw);
+    const float* __restrict__ src = masks + (1LL * k * N + n) * img + 1LL * si0 * S + sj0;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr < sh && c4 < sw) v[k] = __ldg(reinterpret_cast<const float4*>(src + 1LL * rr * S + c4));
+    int o_i, o_j, r_i, r_j, c_i, c_j;
+    d4_src(inv_ops[k], S, i0, j0, &o_i, &o_j);
+    d4_src(inv_ops[k], S, i0 + 1, j0, &r_i, &r_j);
+    d4_src(inv_ops[k], S, i0, j0 + 1, &c_i, &c_j);
+    step_r[k] = (r_i - o_i) * PITCH + (r_j - o_j);
+    step_j[k] = (c_i - o_i) * PITCH + (c_j - o_j);
+    base[k] = (o_i - si0) * PITCH + (o_j - sj0);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float* row = &t[k][rr * PITCH + c4];
+    row[0] = v[k].x, row[1] = v[k].y, row[2] = v[k].z, row[3] = v[k].w;
+  }
+  __syncthreads();
+  const int i = i0 + rr, j = j0 + c4;
+  if (i <= i1 && j <= j1) {  // (S % 4 == 0: a group of four columns is inside or outside as a whole)
+    float res[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        acc += static_cast<double>(t[k][base[k] + rr * step_r[k] + (c4 + e) * step_j[k]]);
+      res[e] = static_cast<float>(acc / 6.0);
+    }
+    *reinterpret_cast<float4*>(out + n * img + 1LL * i * S + j) = make_float4(res[0], res[1], res[2], res[3]);
+  }
+}
+
 // Windows of a batch of images addressed by a device job table: job j copies the win x win window
 // of image jobs[j].x whose top-left pixel is (jobs[j].y, jobs[j].z) -- pixels outside the image
 // read as zero -- into window jobs[j].w of `out`.  One block per (job, window row).  Serves both
@@ -667,7 +799,20 @@ int rsu_d4_transform(const void* in, void* out, int N, int S, int pixel_bytes,
   const dim3 g32((S + 31) / 32, (S + 31) / 32, N), g64((S + 63) / 64, (S + 63) / 64, N);
   const bool word4 = pixel_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 3) == 0;
-  if (word4 && pixel_bytes == 12) {  // RGB fp32
+  const bool vec16 = word4 && (1LL * S * pixel_bytes) % 16 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec16 && pixel_bytes == 12) {  // RGB fp32, 16-byte accesses
+    d4_transform_vec_kernel<uint32_t, 3, 32, uint4><<<g32, block, 0, st>>>(
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops, n_in);
+  } else if (vec16 && pixel_bytes == 4) {  // fp32 masks, 16-byte accesses
+    d4_transform_vec_kernel<uint32_t, 1, 64, uint4><<<g64, block, 0, st>>>(
+        static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops, n_in);
+  } else if (pixel_bytes == 1 && S % 4 == 0 &&
+             ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
+    // uint8 label masks, 4 pixels per access
+    d4_transform_vec_kernel<uint8_t, 1, 64, uint32_t><<<g64, block, 0, st>>>(
+        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), S, ops, n_in);
+  } else if (word4 && pixel_bytes == 12) {  // RGB fp32
     d4_transform_kernel<uint32_t, 3, 32><<<g32, block, 0, st>>>(
         static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), S, ops, n_in);
   } else if (word4 && pixel_bytes == 4) {  // fp32 masks
@@ -772,7 +917,10 @@ int rsu_ensemble_invert(const float* masks, int N, int S, float* out, void* stre
   if (N < 1 || S < 1) return set_error(RSU_EINVAL, "ensemble_invert: shape");
   if (N > 65535) return set_error(RSU_EINVAL, "ensemble_invert: N > 65535");
   const dim3 grid((S + 31) / 32, (S + 31) / 32, N), block(32, 8);
-  ensemble_invert_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(masks, N, S, out);
+  if (S % 4 == 0 && ((reinterpret_cast<uintptr_t>(masks) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    ensemble_invert_vec_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(masks, N, S, out);
+  else
+    ensemble_invert_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(masks, N, S, out);
   return check_launch("ensemble_invert");
 }
 

@@ -89,14 +89,15 @@ class PeerOptimizer:
             return 0
         return base + (tensor.data_ptr() - int(handle.buffer_ptrs[handle.rank]))
 
-    def step(self, net, lr, momentum):
-        """All ranks' gradients -> one update of this rank's slices -> everybody's weights."""
+    def step(self, net, lr, momentum, extra_scale=1.0):
+        """All ranks' gradients -> one update of this rank's slices -> everybody's weights.
+        extra_scale: additional factor on the summed gradient (1 / micro-batches)."""
         self._hg.barrier(channel=0)          # every rank's backward pass has finished
         lib = _lib.load()
         stream = _lib.stream_ptr()
         for lo, hi in rank_slices(net.live_ranges(), self.rank, self.world):
             _lib.check(lib.rsu_dp_momentum_sgd(C.byref(self._peers), C.c_void_p(net.momentum.data_ptr()),
-                                               lo, hi, float(lr), float(momentum), 1.0 / self.world, stream))
+                                               lo, hi, float(lr), float(momentum), float(extra_scale) / self.world, stream))
         self._hp.barrier(channel=1)          # every rank's weights (and gradient reads) are complete
 
     def full_momentum(self, net):

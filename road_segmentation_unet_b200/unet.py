@@ -673,13 +673,31 @@ class UNet:
         weights)."""
         lr = self.learning_rate(lr0)
         if peer is not None:
-            peer.step(self, lr, momentum)
+            peer.step(self, lr, momentum, extra_scale=grad_scale)
         else:
             for a, b in self.live_ranges():
                 ops.momentum_sgd(self.params[a:b], self.momentum[a:b], self.grads[a:b], lr, momentum,
                                  grad_scale)
         self.global_step += 1
         self.pack_weights()
+
+    def accumulate_step(self, micro_batches, lr0=0.01, momentum=0.9, keep=1.0, peer=None, finish=None):
+        """One optimizer step over several micro-batches [(images, labels), ...] of this engine's
+        batch size: gradients accumulate in the flat fp32 vector (every weight-gradient kernel adds
+        into it) and the update uses their mean -- a global batch that does not fit in HBM at once
+        (2052^2 patches: ~20 GB of activations each).  peer / finish: the data-parallel exchange
+        (dp.PeerOptimizer, or a callable that completes the bucketed all-reduce and returns its
+        scale); the bucket hook only fires during the last micro-batch."""
+        hook = self.on_bucket_ready
+        self.zero_grads()
+        for i, (images, labels) in enumerate(micro_batches):
+            self.on_bucket_ready = hook if i == len(micro_batches) - 1 else None
+            self.forward(images, labels, keep)
+            self.backward()
+        self.on_bucket_ready = hook
+        scale = (finish() if finish is not None else 1.0) / len(micro_batches)
+        self.apply_gradients(lr0, momentum, scale, peer=peer)
+        return self.loss
 
     def train_step(self, images, labels, lr0=0.01, momentum=0.9, keep=1.0, allreduce=None):
         """forward + backward + momentum update; returns the device scalar loss tensor."""

@@ -120,10 +120,18 @@ def test_ensemble(images):
     m = np.random.RandomState(5).rand(2, 37, 37, 1).astype(np.float32)
     rt = images.invert_image_augmentation_ensemble(images.image_augmentation_ensemble(m))
     assert np.abs(rt - m).max() <= 1e-6
+    for side in (604, 68):  # 16-byte path incl. partial edge tiles, random (not round-trip) masks
+        big = np.random.RandomState(6).rand(12, side, side, 1).astype(np.float32)
+        want = IO.invert_image_augmentation_ensemble(big.astype(np.float64).copy())
+        assert np.abs(images.invert_image_augmentation_ensemble(big) - want).max() <= 1e-6
 
 
 @pytest.mark.parametrize("dtype,shape", [(torch.float32, (9, 50, 50, 3)), (torch.uint8, (8, 37, 37)),
-                                          (torch.float32, (8, 764, 764, 3))])
+                                          (torch.float32, (8, 764, 764, 3)),
+                                          # 16-byte / 4-byte vector paths incl. partial edge tiles
+                                          (torch.float32, (8, 604, 604, 3)), (torch.float32, (8, 604, 604)),
+                                          (torch.float32, (16, 68, 68, 1)), (torch.uint8, (16, 388, 388)),
+                                          (torch.uint8, (8, 100, 100)), (torch.float32, (8, 36, 36, 3))])
 def test_d4_transform(images, dtype, shape):
     """All 8 dihedral elements, bit-exact: out = rot90(flipud(x) if op & 4 else x, k = op & 3)
     (tf.image.flip_up_down / rot90 of tf_aerial_images.py:173-210, np.flip / np.rot90 of

@@ -455,3 +455,33 @@ def test_flagship_free_running_batch4():
                                                 "conv_dilut_1/", "conv_9/", "conv_10/", "up_conv_3", "up_conv_4",
                                                 "weight_output"))]
     assert all(e32[n] < TOL for n in shallow), {n: e32[n] for n in shallow if not e32[n] < TOL}
+
+
+def test_large_tile_forward_parity():
+    """BASELINE.json configs[4], tiles as patches: the 6-layer dilated root-64 U-Net on a 1404^2
+    input (P = 1028, the valid patch size next to 1024) -- every activation, the logits and
+    P(road) of the device forward pass within 2e-2 of the fp32 oracle."""
+    from road_segmentation_unet_b200 import unet
+    L, root, dil, P, B = 6, 64, True, 1028, 1
+    S = unet.input_size_needed(P, L)
+    assert S == 1404
+    params = make_params(L, root, dil)
+    X, _ = synth(B, S, P, seed=5)
+    acts = {}
+    with torch.no_grad():
+        logits = O.forward(torch.tensor(X), O.to_torch(params), L, root, dil, acts=acts)
+        probs32 = torch.softmax(logits, dim=3)[..., 1].numpy()
+    net = unet.UNet(L, root, dil, B, S, params=params, training=False)
+    assert net.P == P
+    net.forward(torch.tensor(X).cuda(), keep=1.0, want_logits=True)
+    torch.cuda.synchronize()
+    errs = {"logits": rel(net.logits.cpu().numpy(), logits.numpy()), "probs": rel(net.probs.cpu().numpy(), probs32)}
+    for i in range(L):
+        errs["conv_%d/relu2" % i] = rel(net.A2[i].float().cpu().numpy(), acts["conv_%d/relu2" % i].numpy())
+        if i < L - 1:
+            ref = O.center_crop(acts["conv_dilut_%d/relu2" % i], net.up_size[L - 2 - i])
+            errs["conv_dilut_%d/relu2" % i] = rel(net.D2[i].float().cpu().numpy(), ref.numpy())
+    for j in range(L - 1):
+        errs["conv_%d/relu2" % (L + j)] = rel(net.C2[j].float().cpu().numpy(), acts["conv_%d/relu2" % (L + j)].numpy())
+    print("P = 1028 activations vs fp32, worst:", sorted(errs.items(), key=lambda kv: -kv[1])[:4])
+    assert max(errs.values()) < TOL, errs

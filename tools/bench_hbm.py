@@ -53,7 +53,7 @@ def timed(fn, reps=5, flush=True):
     return best
 
 
-def run(n_img=24):
+def run(n_img=48):  # BASELINE.json configs[2] with N = 8 images: 8 x 6 ensemble variants
     peak, src = peak_gbs()
     rows = []
 
@@ -89,19 +89,24 @@ def run(n_img=24):
     add("extract_patches", (padded.numel() + out.numel()) * 4, ms,
         "128 patches 764^2x3 fp32 out of one 980^2 image, stride 12: source read once + patches written once")
 
-    preds = torch.rand(361, 388, 388, 1, device="cuda", generator=g)
-    ms = timed(lambda: images.images_from_patches_dev(preds, 1, 19, 12))
-    add("overlap_average", preds.numel() * 4 + 604 * 604 * 4, ms, "361 patches 388^2 -> 604^2, stride 12")
+    # one predict() call of configs[2]: the 6 ensemble variants of a 604^2 image, 361 patches each
+    preds = torch.rand(6 * 361, 388, 388, 1, device="cuda", generator=g)
+    ms = timed(lambda: images.images_from_patches_dev(preds, 6, 19, 12))
+    add("overlap_average", preds.numel() * 4 + 6 * 604 * 604 * 4, ms,
+        "6 x 361 patches 388^2 -> 6 x 604^2, stride 12 (one predict call)")
+    del preds
 
-    pad = images.mirror_border_dev(x[:8, :400, :400].contiguous(), 216)
+    # one angle of the README training-set preparation: 100 images 400^2, offset 188 (images.py:320-351)
+    pad = images.mirror_border_dev(torch.rand(100, 400, 400, 3, device="cuda", generator=g), 216)
     ms = timed(lambda: images.rotate_crop_dev(pad, 30, 776))
-    add("rotate_nn_crop", 8 * (832 ** 2 + 776 ** 2) * 3 * 4, ms, "8x832^2x3 -> 776^2, 30 deg")
+    add("rotate_nn_crop", 100 * (832 ** 2 + 776 ** 2) * 3 * 4, ms, "100x832^2x3 -> 776^2, 30 deg")
+    del pad
 
     probs = torch.rand(96, 608, 608, device="cuda", generator=g)
     ms = timed(lambda: images.patch_vote_dev(probs, 16, images.RULE_VOTE, 0.25, quantized=True, labels=True))
     add("patch_vote (quantize_mask)", 2 * probs.numel() * 4, ms, "96x608^2 fp32 -> quantised masks + 38x38 labels")
 
-    masks = torch.rand(6 * 16, 604, 604, device="cuda", generator=g)
+    masks = torch.rand(6 * 16, 604, 604, device="cuda", generator=g)  # two predict calls' worth
     ms = timed(lambda: images.invert_image_augmentation_ensemble_dev(masks))
     add("ensemble_invert", masks.numel() * 4 + 16 * 604 * 604 * 4, ms, "96x604^2 -> 16x604^2")
 

@@ -306,7 +306,7 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
   if (d->pool_done_host) *d->pool_done_host = 0;
   // Halo-tile kernel for the layers whose per-tap operand traffic (L2 -> SM) bounds them: few
   // output channels per tile and a large pixel grid.
-  // (thresholds from the per-layer A/B table, profiles/r1_layers_ab.md)
+  // (thresholds from the per-layer A/B table, profiles/r2_halo_experiments.txt)
   const bool want_halo =
       d->algo == 2 ||
       (d->algo == 0 && d->n_taps == 9 && d->H_out >= 64 && d->W_out >= 64 &&

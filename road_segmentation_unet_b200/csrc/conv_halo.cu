@@ -10,7 +10,7 @@
 // swizzle is a function of the absolute shared-memory address, so a window may start at any row
 // (tools/diag_swizzle.cu is the hardware probe for this).  Per 64-channel chunk the L2 -> SM
 // traffic of A drops from 9 x 16 KiB to 22.5 KiB per 128 pixels, which is what bounds the
-// Cout <= 128 layers of the network (profiles/r1_conv_gemm_legacy.md).
+// Cout <= 128 layers of the network (profiles/r1_layers.json, per-tap vs halo columns of profiles/r2_halo_experiments.txt).
 //
 // MT = 2 gives two accumulators (256 pixels) per weight tile, halving the B traffic; when the
 // whole weight matrix of a CTA's N tile fits in shared memory next to the A ring it is loaded

@@ -77,7 +77,11 @@ __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const void* map, uint
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(bar));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote)
+  // relaxed: the barrier only tells the MMA thread that this CTA's tcgen05.ld of the accumulator
+  // have completed (tcgen05.wait::ld + fence::before_thread_sync above).  A release at cluster
+  // scope compiles to MEMBAR.ALL.GPU, i.e. the epilogue warp would wait once per tile until all
+  // of its global stores / reductions have drained.
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote)
                : "memory");
 }
 }  // namespace pair

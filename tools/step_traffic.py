@@ -1,5 +1,5 @@
 """DRAM traffic per training step by kernel class from the per-launch ncu pass
-(`tools/profile_round.sh` -> gpurun_out/step_metrics_raw.csv).  Writes profiles/r1_step_traffic.json,
+(`tools/profile_round.sh` -> gpurun_out/step_metrics_raw.csv).  Writes profiles/r2_step_traffic.json,
 which bench.py reports as roofline.traffic.  Usage: python tools/step_traffic.py raw.csv out.json"""
 import csv
 import json

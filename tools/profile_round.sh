@@ -24,7 +24,7 @@ if [ "$PER" -gt 0 ]; then
 fi
 for K in "$@"; do
   # K = kernel-regex:skip:count, e.g. conv_halo_kernel:40:2, conv_gemm2_kernel:150:4
-  # (round 2: conv_gemm2_kernel:150:4 conv_halo_kernel:66:3 wgrad_gemm_kernel:69:3 wgrad_halo_kernel:36:3)
+  # (round 2: conv_gemm2_kernel:150:3 conv_halo_kernel:68:3 wgrad_gemm2_kernel:55:2 wgrad_halo_kernel:32:2 wgrad_gemm_kernel:26:2)
   IFS=: read -r NAME SKIP CNT <<< "$K"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$NAME \
     --launch-skip $SKIP -c $CNT -o $OUT/full_$NAME -f $BENCH > $OUT/full_$NAME.log 2>&1

@@ -53,11 +53,12 @@ class PeerOptimizer:
         self.grads.zero_()
         self._hp = symm.rendezvous(self.params, name)
         self._hg = symm.rendezvous(self.grads, name)
-        # RSU_DP_MULTICAST: 0 = peer loads / stores only (default: as fast as NVLS at 2 and at 8
-        # GPUs, profiles/r2_dp_n2.txt / r2_dp_n8.txt -- every rank has to receive (world-1)/world
-        # of the fp32 weights either way), 1 = NVLS for both directions, 2 = multimem.ld_reduce for
-        # the gradients only, 3 = multimem.st for the weights only
-        mc_mode = int(os.environ.get("RSU_DP_MULTICAST", "0"))
+        # RSU_DP_MULTICAST: 0 = peer loads / stores only, 1 = NVLS for both directions
+        # (multimem.ld_reduce for the gradients, multimem.st for the weights), 2 / 3 = loads / stores
+        # only; default "auto" = 1 from four ranks on (profiles/r2_dp_n2.txt / r2_dp_n8.txt: equal at
+        # 2 GPUs, ~0.2 ms per step better at 8 -- the switch carries 1/world of the traffic per rank)
+        mc_env = os.environ.get("RSU_DP_MULTICAST", "auto")
+        mc_mode = (1 if world >= 4 else 0) if mc_env == "auto" else int(mc_env)
         want_mc = mc_mode != 0
         peers = _lib.DpPeers()
         peers.world, peers.rank = world, rank
@@ -71,6 +72,10 @@ class PeerOptimizer:
         peers.params_mc = mc_p if self.multicast and mc_mode in (1, 3) else None
         self.mc_mode = mc_mode if self.multicast else 0
         self._peers = peers
+        # RSU_DP_OVERLAP=0: one exchange after the whole backward pass instead of per bucket
+        self.overlap = os.environ.get("RSU_DP_OVERLAP", "1") != "0"
+        self._side = torch.cuda.Stream()
+        self._armed, self._done, self._acc = None, [], None
 
     @staticmethod
     def _peer_ptr(handle, tensor, r):
@@ -89,22 +94,75 @@ class PeerOptimizer:
             return 0
         return base + (tensor.data_ptr() - int(handle.buffer_ptrs[handle.rank]))
 
-    def step(self, net, lr, momentum, extra_scale=1.0):
-        """All ranks' gradients -> one update of this rank's slices -> everybody's weights.
-        extra_scale: additional factor on the summed gradient (1 / micro-batches)."""
-        self._hg.barrier(channel=0)          # every rank's backward pass has finished
+    # ---- overlapped exchange: buckets are exchanged on a side stream while the backward pass runs
+    def arm(self, lr, momentum, extra_scale=1.0):
+        """Called before a backward pass: from now on every finished bucket of the flat gradient
+        (UNet.on_bucket_ready) is exchanged right away on the side stream -- the kernel needs no
+        shared memory and few registers, so its blocks co-reside with the persistent tensor-core
+        kernels of the layers that are still being differentiated."""
+        self._armed = (float(lr), float(momentum), float(extra_scale))
+        self._done = []
+
+    def bucket_ready(self, lo, hi):
+        if getattr(self, "_armed", None) is None or not self.overlap:
+            return
+        lr, momentum, scale = self._armed
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self._hg.barrier(channel=0)      # every rank has finished this bucket's gradients
+            self._launch([(lo, hi)], lr, momentum, scale)
+        self._done.append((lo, hi))
+
+    def _launch(self, ranges, lr, momentum, scale):
         lib = _lib.load()
         stream = _lib.stream_ptr()
-        for lo, hi in rank_slices(net.live_ranges(), self.rank, self.world):
-            _lib.check(lib.rsu_dp_momentum_sgd(C.byref(self._peers), C.c_void_p(net.momentum.data_ptr()),
-                                               lo, hi, float(lr), float(momentum), float(extra_scale) / self.world, stream))
+        for lo, hi in rank_slices(ranges, self.rank, self.world):
+            _lib.check(lib.rsu_dp_momentum_sgd(C.byref(self._peers), C.c_void_p(self._acc.data_ptr()),
+                                               lo, hi, lr, momentum, scale / self.world, stream))
+
+    def buckets(self, net):
+        """The exchange units: the live pieces of the backward pass's gradient buckets, in flat
+        order.  Ownership (which rank updates which elements, and holds their momentum) is always
+        the per-bucket split of rank_slices, whether a bucket is exchanged during the backward pass
+        or afterwards."""
+        if getattr(self, "_buckets", None) is None:
+            enc, dec = net._bucket_bounds()
+            out = []
+            for lo, hi in enc + dec:
+                for a, b in net.live_ranges():
+                    if min(b, hi) > max(a, lo):
+                        out.append((max(a, lo), min(b, hi)))
+            self._buckets = sorted(out)
+        return self._buckets
+
+    def owned(self, net):
+        return [s for b in self.buckets(net) for s in rank_slices([b], self.rank, self.world)]
+
+    def step(self, net, lr, momentum, extra_scale=1.0):
+        """All ranks' gradients -> one update of this rank's slices -> everybody's weights: the
+        buckets that were not already exchanged during the backward pass, then the barrier after
+        which every replica holds the new weights."""
+        self._acc = net.momentum
+        done = set(getattr(self, "_done", []))
+        rest = [b for b in self.buckets(net) if b not in done]
+        assert all(d in self.buckets(net) for d in done)
+        cur = torch.cuda.current_stream()
+        if done:
+            cur.wait_stream(self._side)
+        if rest:
+            self._hg.barrier(channel=0)      # every rank's backward pass has finished
+            for b in rest:
+                self._launch([b], float(lr), float(momentum), float(extra_scale))
         self._hp.barrier(channel=1)          # every rank's weights (and gradient reads) are complete
+        self._armed, self._done = None, []
 
     def full_momentum(self, net):
         """The complete momentum vector (every rank holds its own slices): one all-reduce of the
         slices into a scratch vector, for checkpoints."""
         full = torch.zeros_like(net.momentum)
-        for lo, hi in rank_slices(net.live_ranges(), self.rank, self.world):
+        for lo, hi in self.owned(net):
             full[lo:hi].copy_(net.momentum[lo:hi])
         self.dist.all_reduce(full)
         return full

@@ -307,6 +307,11 @@ class ConvolutionalModel:
             if self._dist.active and self._peer is None else None
         if self._reducer is not None:
             self._net.on_bucket_ready = self._reducer.bucket_ready
+        if self._peer is not None:
+            self._peer._acc = self._net.momentum
+            self._net.on_bucket_ready = self._peer.bucket_ready
+            self._net.on_backward_begin = lambda scale=1.0: self._peer.arm(
+                self._net.learning_rate(opts.lr), opts.momentum, scale)
 
     @property
     def net(self):

@@ -143,6 +143,7 @@ class UNet:
         # data-parallel hook: called as on_bucket_ready(start, end) when the flat-gradient slice
         # [start, end) is final, so its all-reduce overlaps the rest of the backward pass
         self.on_bucket_ready = None
+        self.on_backward_begin = None  # called at the start of backward() (arms the exchange)
         self._plan_geometry()
         self._flops = {k: v * batch_size for k, v in
                        plan_flops(num_layers, root_size, dilated_layers, self.P).items()}
@@ -579,6 +580,8 @@ class UNet:
         L, f = self.L, self.f
         keep = self._keep
         drop = keep < 1.0
+        if self.on_backward_begin is not None and self.on_bucket_ready is not None:
+            self.on_backward_begin(getattr(self, "_bwd_scale", 1.0))
         enc_buckets, dec_buckets = self._bucket_bounds()
         for j in range(L - 2, -1, -1):
             i = L - 2 - j
@@ -690,11 +693,13 @@ class UNet:
         scale); the bucket hook only fires during the last micro-batch."""
         hook = self.on_bucket_ready
         self.zero_grads()
+        self._bwd_scale = 1.0 / len(micro_batches)  # what an exchange armed during backward() applies
         for i, (images, labels) in enumerate(micro_batches):
             self.on_bucket_ready = hook if i == len(micro_batches) - 1 else None
             self.forward(images, labels, keep)
             self.backward()
         self.on_bucket_ready = hook
+        self._bwd_scale = 1.0
         scale = (finish() if finish is not None else 1.0) / len(micro_batches)
         self.apply_gradients(lr0, momentum, scale, peer=peer)
         return self.loss

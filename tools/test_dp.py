@@ -107,7 +107,8 @@ def main():
     # ---- 2. timing at the flagship config
     if args.flagship:
         cfg = dict(num_layers=6, patch_size=388, batch_size=32, lr=0.01)
-        for mode, multicast in (("nccl", 0), ("peer", 0), ("peer", 1)):
+        for mode, multicast, overlap in (("nccl", 0, 1), ("peer", 0, 0), ("peer", 0, 1), ("peer", 1, 1)):
+            os.environ["RSU_DP_OVERLAP"] = str(overlap)
             m, o = make(mode, multicast, **cfg)
             if mode == "peer" and multicast and not m._peer.multicast:
                 continue
@@ -115,19 +116,20 @@ def main():
             x = torch.rand(32, m.input_size, m.input_size, 3, device="cuda")
             y = (torch.rand(32, 388, 388, device="cuda") < 0.3).to(torch.uint8)
 
+            hook = net.on_bucket_ready
+
             def step(exchange=True):
+                net.on_bucket_ready = hook if exchange else None
                 net.zero_grads()
                 net.forward(x, y, keep=1.0)
                 net.backward()
                 if exchange:
                     m.apply_update()
                 else:
-                    if m._reducer is not None:
-                        m._reducer.finish()
                     net.apply_gradients(o.lr, o.momentum, 1.0)
 
             res = {}
-            for tag, ex in (("with exchange", True),) + ((("local update only", False),) if mode == "peer" else ()):
+            for tag, ex in (("with exchange", True),) + ((("local update only", False),) if mode == "peer" and not overlap else ()):
                 for _ in range(3):
                     step(ex)
                 dist.barrier()
@@ -141,7 +143,8 @@ def main():
                 t = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 res[tag] = float(t.item())
-            log("flagship step, %d GPUs, %-5s%s: %s" % (world, mode, " + multicast mode %d" % multicast if multicast else "",
+            log("flagship step, %d GPUs, %-5s%s%s: %s" % (world, mode, " + multicast mode %d" % multicast if multicast else "",
+                                                          " (exchange %s)" % ("overlapped with the backward pass" if overlap else "after the backward pass") if mode == "peer" else "",
                                                         ", ".join("%s %.2f ms" % kv for kv in res.items())))
             del m, net, x, y
             torch.cuda.empty_cache()

@@ -82,7 +82,8 @@ typedef struct {
   int accumulate; /* out += result */
   int algo;       /* 0 = choose, 1 = one TMA box per tap, 2 = halo tile shared by all taps,
                      3 = algorithm 1 on CTA pairs (tcgen05.mma.cta_group::2, N tile 128 / 256;
-                     chosen by 0 whenever algorithm 1 would run with the 256-wide N tile) */
+                     chosen by 0 whenever algorithm 1 would run with the 256-wide N tile),
+                     4 = algorithm 2 on CTA pairs (each CTA keeps half of the resident weights) */
   /* mask_nc > 0: the mask tensor has mask_nc channels and covers output channels
    * [mask_c0, mask_c0 + mask_nc) only (the ReluGrad of one member of a concat gradient,
    * unet.py:70-85); both multiples of the N tile (64 / 128 / 256, the largest dividing Ntot). */

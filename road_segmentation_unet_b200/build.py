@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librsu_b200.so")
-SOURCES = ["host_common.cu", "conv_gemm.cu", "conv_gemm2.cu", "conv_halo.cu", "wgrad_gemm.cu", "wgrad_gemm2.cu", "wgrad_halo.cu",
+SOURCES = ["host_common.cu", "conv_gemm.cu", "conv_gemm2.cu", "conv_halo.cu", "conv_halo2.cu", "wgrad_gemm.cu", "wgrad_gemm2.cu", "wgrad_halo.cu",
            "conv_first.cu", "elementwise.cu", "geometry.cu", "peer_sgd.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

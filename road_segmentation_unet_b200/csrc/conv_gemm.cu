@@ -278,6 +278,7 @@ static int conv_smem_bytes(int BN, int num_k, int* stages_out) {
 }
 
 int launch_conv_halo(const rsu_conv_gemm_desc* d, cudaStream_t stream, bool forced);  // conv_halo.cu
+int launch_conv_halo2(const rsu_conv_gemm_desc* d, cudaStream_t stream);               // conv_halo2.cu
 int launch_conv_gemm2(ConvGemmParams& p, const void* weights, int ktot, int ntot,
                       cudaStream_t stream);  // conv_gemm2.cu
 
@@ -311,6 +312,19 @@ extern "C" int rsu_conv_gemm(const rsu_conv_gemm_desc* d, void* stream_) {
       d->algo == 2 ||
       (d->algo == 0 && d->n_taps == 9 && d->H_out >= 64 && d->W_out >= 64 &&
        (d->Ntot <= 192 || (d->Ntot <= 384 && d->Ntot % 128 == 0 && d->H_out >= 190)));
+  // CTA-pair halo kernel (conv_halo2.cu) wherever the halo kernel is wanted and the pair's halved
+  // weight footprint fits in shared memory: x1.0 - 2.1 on the N = 64 / 128 layers of the flagship
+  // network (tools/bench_halo_pair.py, profiles/r2_halo_pair_ab.txt); explicit with algo 4.
+  // RSU_HALO_PAIR=0 disables.
+  static const bool halo_pair_auto = [] {
+    const char* e = getenv("RSU_HALO_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  if (d->algo == 4 || (want_halo && d->algo == 0 && halo_pair_auto)) {
+    const int rc = launch_conv_halo2(d, stream);
+    if (rc >= 0) return rc;
+    if (d->algo == 4) return set_error(RSU_EINVAL, "shape not eligible for the CTA-pair halo kernel");
+  }
   if (want_halo) {
     const int rc = launch_conv_halo(d, stream, d->algo == 2);
     if (rc >= 0) return rc;

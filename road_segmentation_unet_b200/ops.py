@@ -69,7 +69,7 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-ALGO_AUTO, ALGO_PER_TAP, ALGO_HALO, ALGO_PER_TAP_PAIR = 0, 1, 2, 3
+ALGO_AUTO, ALGO_PER_TAP, ALGO_HALO, ALGO_PER_TAP_PAIR, ALGO_HALO_PAIR = 0, 1, 2, 3, 4
 
 
 def conv_gemm(srcs, taps, weights, out, n_out, bias=None, relu=False, mask=None, accumulate=False,

@@ -650,3 +650,50 @@ def test_dp_momentum_sgd_single_rank(ops):
     ops.fill_zero(z[64:128])
     torch.cuda.synchronize()
     assert float(z[64:128].abs().max()) == 0.0 and np.array_equal(z.cpu().numpy()[:64], w0[:64])
+
+
+@pytest.mark.parametrize("case", [
+    # (N, H, Cin, Cout, dilation)
+    (2, 70, 64, 64, 1),     # N = 64: 32 weight rows per CTA, fused pool, even / odd block counts
+    (1, 76, 64, 128, 1),    # N = 128, 68 = 8.5 tiles wide: ragged edges
+    (3, 72, 128, 64, 2),    # two input chunks, dilation 2, odd number of spatial blocks
+    (1, 100, 192, 64, 1),   # three chunks (conv_10/conv1 shape class)
+])
+def test_conv3x3_halo_cta_pair(ops, case):
+    """conv_halo2_kernel (halo tiles on CTA pairs, algo 4) against the single-CTA halo kernel
+    (algo 2): same dot products in the same K order -> identical outputs.  Forward with bias +
+    ReLU + fused 2x2 max pool, and the data gradient with the ReLU-gradient mask."""
+    n, h, cin, cout, d = case
+    rs = np.random.RandomState(57)
+    x = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    w = bf((rs.randn(3, 3, cin, cout) / np.sqrt(9 * cin)).astype(np.float32))
+    b = rs.randn(cout).astype(np.float32)
+    ho = h - 2 * d
+    outs, pools = [], []
+    for algo in (ops.ALGO_HALO, ops.ALGO_HALO_PAIR):
+        out = torch.full((n, ho, ho, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+        pool = torch.full((n, ho // 2, ho // 2, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+        pooled = ops.conv3x3_fwd([(dev(x), 0, 0)], pack_fwd(ops, w), dev(b, torch.float32), out, dilation=d,
+                                 algo=algo, pool_out=pool if ho % 2 == 0 else None)
+        torch.cuda.synchronize()
+        outs.append(out.float().cpu().numpy())
+        pools.append(pool.float().cpu().numpy() if pooled else None)
+    ref = torch.relu(O.conv2d_valid(torch.tensor(x), torch.tensor(w), torch.tensor(b), d)).numpy()
+    assert rel_err(outs[1], ref) < 6e-3
+    assert np.array_equal(outs[0], outs[1])
+    if ho % 2 == 0:
+        assert pools[1] is not None
+        if pools[0] is not None:  # (the single-CTA kernel only pools in its TMA-store configuration)
+            assert np.array_equal(pools[0], pools[1])
+        want = ref.reshape(n, ho // 2, 2, ho // 2, 2, cout).max(axis=(2, 4))
+        assert rel_err(pools[1], want) < 6e-3
+    # data gradient with the ReLU-gradient mask of the layer input
+    dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
+    mask_src = bf(rs.randn(n, h, h, cin).astype(np.float32))
+    grads = []
+    for algo in (ops.ALGO_HALO, ops.ALGO_HALO_PAIR):
+        out = torch.full((n, h, h, cin), 3.0, dtype=torch.bfloat16, device="cuda")
+        ops.conv3x3_dgrad(dev(dz), pack_dgrad(ops, w), out, dilation=d, mask=dev(mask_src), algo=algo)
+        torch.cuda.synchronize()
+        grads.append(out.float().cpu().numpy())
+    assert np.array_equal(grads[0], grads[1])

@@ -633,7 +633,7 @@ def run_gpu(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
     if rank == 0 and roof is not None:
-        conv_names = ("conv_gemm_kernel", "conv_gemm2_kernel", "conv_halo_kernel", "first_conv_kernel")
+        conv_names = ("conv_gemm_kernel", "conv_gemm2_kernel", "conv_halo_kernel", "conv_halo2_kernel", "first_conv_kernel")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f)

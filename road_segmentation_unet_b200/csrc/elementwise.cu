@@ -941,13 +941,8 @@ int rsu_bias_grad(const rsu_view* v, float* out, void* stream) {
   int k = 256 / G;
   if (k < 1) k = 1;
   if (1LL * v->N * v->H > 0x7fffffffLL) return set_error(RSU_EINVAL, "bias_grad: too many rows");
-  // every block ends with C global atomics, all blocks on the same C addresses: small tensors (the
-  // deep layers: a few hundred image rows) take four rows per block, so that the atomics do not
-  // outweigh the loads (one block per row: 20 - 60 us for a few MB); at least one block per SM
-  const long long rows = 1LL * v->N * v->H;
+  long long blocks = 1LL * v->N * v->H;
   const long long cap = 1LL * num_sms() * 8;
-  long long blocks = rows / 4;
-  if (blocks < num_sms()) blocks = rows < num_sms() ? rows : num_sms();
   if (blocks > cap) blocks = cap;
   bias_grad_kernel<<<static_cast<int>(blocks), G * k, G * 8 * sizeof(float), (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(v->ptr), v->sn, v->sy, v->sx, v->N, v->H, v->W, G, k, out);

@@ -26,7 +26,7 @@ for r in rd[2:]:
     t = float(r[pos["gpu__time_duration.sum"]].replace(",", ""))
     c["time_ns"] += t * {"ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}.get(
         units[pos["gpu__time_duration.sum"]], 1)
-conv = sum(v["dram_bytes"] for k, v in cls.items() if k in ("conv_gemm_kernel", "conv_gemm2_kernel", "conv_halo_kernel", "first_conv_kernel"))
+conv = sum(v["dram_bytes"] for k, v in cls.items() if k in ("conv_gemm_kernel", "conv_gemm2_kernel", "conv_halo_kernel", "conv_halo2_kernel", "first_conv_kernel"))
 out = {"source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over every launch of one training step "
                  "(tools/profile_round.sh, flagship config, batch 32)",
        "conv_class_dram_bytes_per_step": conv, "by_kernel": cls}

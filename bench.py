@@ -595,7 +595,7 @@ def run_gpu(args):
         wg_tf = wg[0] / (wg[1] * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": conv_tf, "peak": peak_sus, "unit": "TFLOP/s",
                 "frac": conv_tf / peak_sus, "traffic": None,
-                "kernel": "conv_gemm2_kernel / conv_halo_kernel / conv_gemm_kernel (tcgen05 implicit GEMM: forward + data gradients)",
+                "kernel": "conv_gemm2_kernel / conv_halo2_kernel / conv_halo_kernel / conv_gemm_kernel (tcgen05 implicit GEMM: forward + data gradients)",
                 "launches_per_step": conv[2] // kp, "ms_per_step": conv[1] / kp,
                 "alg_flops_per_step": conv[0] / kp,
                 "peak_source": "%s sustained cuBLAS bf16 (MEASURED_PEAKS.json), kernel timed inside a long step" % src}
@@ -605,7 +605,7 @@ def run_gpu(args):
         extra = {
             "roofline_wgrad": {"bound": "tensor", "achieved": wg_tf, "peak": peak_sus, "unit": "TFLOP/s",
                                "frac": wg_tf / peak_sus, "launches_per_step": wg[2] // kp,
-                               "ms_per_step": wg[1] / kp, "kernel": "wgrad_gemm_kernel"},
+                               "ms_per_step": wg[1] / kp, "kernel": "wgrad_gemm2_kernel / wgrad_halo_kernel / wgrad_gemm_kernel"},
             "roofline_network": {"bound": "tensor", "achieved": net_tf, "peak": peak, "unit": "TFLOP/s",
                                  "frac": net_tf / peak, "frac_of_sustained": net_tf / peak_sus,
                                  "alg_flops_per_patch": f_alg,

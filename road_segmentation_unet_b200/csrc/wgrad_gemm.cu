@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 }
 
 int launch_wgrad_halo(const rsu_wgrad_desc* d, cudaStream_t stream, int* bias_done);  // wgrad_halo.cu
-int launch_wgrad_gemm2(WgradParams& p, cudaStream_t stream);                           // wgrad_gemm2.cu
+int launch_wgrad_gemm2(WgradParams& p, float* bias_grad, cudaStream_t stream);         // wgrad_gemm2.cu
 
 // pixels per K step of the per-tap kernel (RSU_WGRAD_TILE = 32 | 64 | 128 overrides, for A/B runs)
 static int wgrad_tile_pixels() {
@@ -387,10 +387,13 @@ extern "C" int rsu_wgrad_gemm(const rsu_wgrad_desc* d, void* stream_) {
   // CTA-pair kernel (tcgen05.mma.cta_group::2, wgrad_gemm2.cu): each CTA of a pair loads half of
   // the gradient tile.  Faster than the single-CTA kernel on every 3x3 layer with a 256-wide
   // gradient tile and a small pixel grid (levels 3..8 of the flagship net: x1.00 - 1.11,
-  // profiles/r2_wgrad_pair_ab.txt).  It has no ones atom: the bias gradient of those layers (a
-  // pass over a few MB) is left to the caller (*bias_done_host stays 0).
-  if (d->algo == 3 || (d->algo == 0 && p.BN == 256 && d->n_taps == 9 && d->H <= 104 && d->W <= 104))
-    return launch_wgrad_gemm2(p, stream);
+  // profiles/r2_wgrad_pair_ab.txt); the bias gradient rides along as one more (ones) unit.
+  if (d->algo == 3 || (d->algo == 0 && p.BN == 256 && d->n_taps == 9 && d->H <= 104 && d->W <= 104)) {
+    p.n_tiles_m = (p.n_atoms + 1) / 2;
+    const int rc = launch_wgrad_gemm2(p, bias_grad, stream);
+    if (rc == RSU_OK && bias_grad && d->bias_done_host) *d->bias_done_host = 1;
+    return rc;
+  }
 
   const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
   const int mn_units = p.n_tiles_m * p.n_tiles_n;

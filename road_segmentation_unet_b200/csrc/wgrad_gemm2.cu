@@ -10,9 +10,11 @@
 // A cluster of two CTAs shares one gradient (B) tile and one pixel range: each CTA owns its own
 // row tile (two 64-row atoms of (tap, 64-channel) blocks: M = 2 x 128 for the pair) and loads
 // HALF of the BN gradient channels; tcgen05.mma.cta_group::2 exchanges the halves.  Both
-// operands are MN-major (K = pixels) exactly as in the single-CTA kernel.  There is no ones atom
-// here: the caller is told that the bias gradient was not produced (bias_done = 0) and runs
-// rsu_bias_grad.
+// operands are MN-major (K = pixels) exactly as in the single-CTA kernel.  BiasAddGrad (the column
+// sums of G) rides along as one more unit per (gradient tile, pixel slice): a pair whose A operand
+// is a constant block of ones in both CTAs (the A descriptor of a cta_group::2 MMA is shared, so
+// the ones cannot take a free atom slot of one CTA as they do in wgrad_gemm.cu); row 0 of the
+// leader's accumulator goes to the bias gradient.
 //
 // Reference op replaced: Conv2DBackpropFilter (src/unet.py:34-45, 67, 88-91).
 #include "gemm_params.h"
@@ -24,6 +26,7 @@ namespace rsu {
 constexpr int kWg2Threads = 256;
 constexpr int kWg2TmemCols = 512;
 constexpr int kWg2AccStride = 256;
+constexpr int kWg2OnesBytes = 4096;  // two 16-row K slices of bf16 ones
 constexpr uint32_t kWg2PeerMask = 0xFEFFFFFFu;  // shared::cluster address of the even CTA of a pair
 
 namespace pair {
@@ -107,7 +110,8 @@ __device__ __forceinline__ Atom2 decode_atom2(const WgradParams& p, int atom, in
 
 // p.n_tiles_m = row tiles of 2 atoms (no ones atom), p.ksplit computed for pairs by the launcher.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
-    wgrad_gemm2_kernel(const __grid_constant__ WgradParams p, int stages, uint32_t atom_bytes) {
+    wgrad_gemm2_kernel(const __grid_constant__ WgradParams p, int stages, uint32_t atom_bytes,
+                       float* bias_grad) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -117,7 +121,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
 
   const int n_b_half = p.BN / 128;  // 64-channel gradient atoms per CTA
   const uint32_t stage_bytes = static_cast<uint32_t>(2 + n_b_half) * atom_bytes;
-  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  const uint32_t ones_base = smem_base + stages * stage_bytes;
+  const uint32_t bar_base = ones_base + kWg2OnesBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
@@ -136,6 +141,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
     // loaded: keep it finite (its accumulator rows are not stored)
     uint32_t* z = reinterpret_cast<uint32_t*>(smem_gen);
     for (uint32_t i = threadIdx.x; i < stages * stage_bytes / 4u; i += kWg2Threads) z[i] = 0u;
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + (ones_base - smem_base));
+    for (uint32_t i = threadIdx.x; i < kWg2OnesBytes / 4u; i += kWg2Threads) ones[i] = 0x3F803F80u;
     fence_proxy_async();
   }
   if (warp == 1 && lane == 0) {
@@ -159,7 +166,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
   for (int s = 0; s < p.n_src; ++s) chunks_total += p.src_chunks[s];
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int pix_tiles = p.n_img * tiles_per_img;
-  const int m_pairs = (p.n_tiles_m + 1) >> 1;
+  // (with a bias gradient the unit list is one pair longer: pair index m_real = the ones unit)
+  const int m_real = (p.n_tiles_m + 1) >> 1;
+  const int m_pairs = m_real + (bias_grad != nullptr ? 1 : 0);
   const int total_units = m_pairs * p.n_tiles_n * p.ksplit;
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int tile_pixels = p.TW * p.TH;
@@ -249,26 +258,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kWg2AccStride;
+      const bool ones_unit = m_pair == m_real;
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_base + stage * stage_bytes;
-          // CTA-relative descriptors: the same offsets are valid in both CTAs of the pair
-          const uint32_t a_lo = desc_lo_sw128(a_addr, atom_bytes);
+          // CTA-relative descriptors: the same offsets are valid in both CTAs of the pair.  The
+          // ones unit reads the constant block (both 64-row atoms, 2 KiB apart) at every K slice.
+          const uint32_t a_lo = ones_unit ? (((ones_base >> 4) & 0x3FFFu) | (128u << 16))
+                                          : desc_lo_sw128(a_addr, atom_bytes);
+          const uint32_t a_step = ones_unit ? 0u : 128u;
           const uint32_t b_lo = desc_lo_sw128(a_addr + 2 * atom_bytes, atom_bytes);
           const uint32_t first = pt != pt0 ? 1u : 0u;
           // 16 pixels (K) per instruction = 16 rows of 128 B = 2 KiB further into every atom
           if (mma_per_tile == 4) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              pair::umma2_bf16_lohi(d_tmem, a_lo + j * 128u, hi, b_lo + j * 128u, hi, idesc,
+              pair::umma2_bf16_lohi(d_tmem, a_lo + j * a_step, hi, b_lo + j * 128u, hi, idesc,
                                     j != 0 ? 1u : first);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (j < mma_per_tile)
-                pair::umma2_bf16_lohi(d_tmem, a_lo + j * 128u, hi, b_lo + j * 128u, hi, idesc,
+                pair::umma2_bf16_lohi(d_tmem, a_lo + j * a_step, hi, b_lo + j * 128u, hi, idesc,
                                       j != 0 ? 1u : first);
             }
           }
@@ -294,8 +307,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
       const uint32_t acc = acc_it & 1u;
       const uint32_t acc_phase = (acc_it >> 1) & 1u;
       const int atom = (2 * m_pair + static_cast<int>(rank)) * 2 + (m >> 6);
-      const bool valid = atom < p.n_atoms && pt1 > pt0;
-      float* orow = p.out + (static_cast<long long>(atom) * 64 + (m & 63)) * p.ldo + n_tile * p.BN;
+      // the ones unit: every row of the leader's accumulator holds the column sums of G; row 0
+      // goes to the bias gradient, the peer's half of the pair has nothing to store
+      const bool is_bias = m_pair == m_real && leader && m == 0;
+      const bool valid = ((m_pair < m_real && atom < p.n_atoms) || is_bias) && pt1 > pt0;
+      float* orow = is_bias ? bias_grad + n_tile * p.BN
+                            : p.out + (static_cast<long long>(atom) * 64 + (m & 63)) * p.ldo + n_tile * p.BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row =
@@ -330,11 +347,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
 // Called from rsu_wgrad_gemm (wgrad_gemm.cu) with maps, taps, tile and output already filled in p
 // (p.n_atoms set, BN chosen); fixes the row-tile count (no ones atom), the split-K factor for
 // pairs and launches clusters of 2.
-int launch_wgrad_gemm2(WgradParams& p, cudaStream_t stream) {
+int launch_wgrad_gemm2(WgradParams& p, float* bias_grad, cudaStream_t stream) {
   if (p.BN != 256 && p.BN != 128)
     return set_error(RSU_EINVAL, "two-CTA weight gradient needs an N tile of 128 or 256 (got %d)", p.BN);
   p.n_tiles_m = (p.n_atoms + 1) / 2;
-  const int m_pairs = (p.n_tiles_m + 1) / 2;
+  const int m_pairs = (p.n_tiles_m + 1) / 2 + (bias_grad != nullptr ? 1 : 0);
   const int pix_tiles = p.n_img * p.tiles_x * p.tiles_y;
   const int mn_units = m_pairs * p.n_tiles_n;
   const int pairs = num_sms() / 2;
@@ -342,10 +359,10 @@ int launch_wgrad_gemm2(WgradParams& p, cudaStream_t stream) {
                            1500.0 + 12.0 * p.BN, 4);
   const int atom_bytes = ((p.TW * p.TH * 128) + 1023) & ~1023;
   const int stage_bytes = (2 + p.BN / 128) * atom_bytes;
-  int stages = (220 * 1024) / stage_bytes;
+  int stages = (220 * 1024 - kWg2OnesBytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
-  const int smem = 1024 + stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+  const int smem = 1024 + stages * stage_bytes + kWg2OnesBytes + 8 * (2 * stages + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     RSU_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm2_kernel,
@@ -356,7 +373,7 @@ int launch_wgrad_gemm2(WgradParams& p, cudaStream_t stream) {
   long long grid = 2LL * pairs;
   if (2 * total < grid) grid = 2 * total;
   wgrad_gemm2_kernel<<<static_cast<unsigned>(grid), kWg2Threads, smem, stream>>>(
-      p, stages, static_cast<uint32_t>(atom_bytes));
+      p, stages, static_cast<uint32_t>(atom_bytes), bias_grad);
   return check_launch("wgrad_gemm2_kernel");
 }
 

@@ -605,13 +605,22 @@ def test_wgrad_cta_pair(ops, case):
     x = bf(rs.randn(n, h, h, cin).astype(np.float32))
     ho = h - 2 * d
     dz = bf(rs.randn(n, ho, ho, cout).astype(np.float32))
-    outs = []
+    outs, biases = [], []
     for algo in (ops.ALGO_PER_TAP, ops.ALGO_PER_TAP_PAIR):
         dw = torch.zeros(9 * cin, cout, dtype=torch.float32, device="cuda")
-        done = ops.conv3x3_wgrad([(dev(x), 0, 0)], dev(dz), dw, dilation=d, bias_grad=None, algo=algo)
+        db = torch.zeros(cout, dtype=torch.float32, device="cuda")
+        done = ops.conv3x3_wgrad([(dev(x), 0, 0)], dev(dz), dw, dilation=d, bias_grad=db, algo=algo)
         torch.cuda.synchronize()
-        assert not done
+        assert done  # BiasAddGrad rides along in both kernels (ones atom / ones unit)
         outs.append(dw.cpu().numpy())
+        biases.append(db.cpu().numpy())
+    assert rel_err(biases[1], dz.sum(axis=(0, 1, 2))) < 2e-3
+    assert rel_err(biases[1], biases[0]) < 1e-5
+    dw = torch.zeros(9 * cin, cout, dtype=torch.float32, device="cuda")  # and without a bias gradient
+    assert not ops.conv3x3_wgrad([(dev(x), 0, 0)], dev(dz), dw, dilation=d, bias_grad=None,
+                                 algo=ops.ALGO_PER_TAP_PAIR)
+    torch.cuda.synchronize()
+    assert rel_err(dw.cpu().numpy(), outs[1]) < 1e-5
     xt = torch.tensor(x)
     w = torch.zeros(3, 3, cin, cout, requires_grad=True)
     O.conv2d_valid(xt, w, None, d).backward(torch.tensor(dz))

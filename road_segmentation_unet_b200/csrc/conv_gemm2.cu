@@ -332,7 +332,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv2Threads, 1)
     }
   }
 
-  // neither CTA may release its shared / tensor memory while the pair's MMAs can still read it
+  // Neither CTA may release its shared / tensor memory while the pair's MMAs can still read it --
+  // and this final cluster barrier is also what keeps the PEER's shared memory alive for the
+  // leader's late multicast arrivals on its empty barriers: the peer's producer has no tail that
+  // waits for them, so nothing else orders the peer's exit after the leader's last commit.
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) tmem_dealloc2(tmem_base, kTmem2Cols);

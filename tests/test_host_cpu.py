@@ -222,6 +222,40 @@ def test_dp_rank_slices_partition_the_live_parameters():
         assert max(sizes) - min(sizes) <= 8
 
 
+def test_dp_exchange_buckets_match_the_backward_pass():
+    """dp.PeerOptimizer exchanges the gradient bucket by bucket while the backward pass runs: the
+    pieces UNet._ready hands to the hook (live parts of the decoder / encoder buckets, in backward
+    order) must be exactly PeerOptimizer.buckets(), they must tile the live ranges, and the
+    per-bucket ownership of all ranks must partition them (no GPU needed: layout logic only)."""
+    import types
+    from road_segmentation_unet_b200 import unet
+    from road_segmentation_unet_b200.dp import PeerOptimizer, rank_slices
+    for L, dil in ((6, True), (4, False), (3, True)):
+        n = types.SimpleNamespace(L=L, dilated=dil, root=64, _live_ranges=None)
+        n.offsets, n.n_flat = unet.flat_layout(L, 64, dil)
+        n._first_offset = lambda prefix, n=n: next(o for name, o in n.offsets.items() if name.startswith(prefix))
+        for meth in ("live_ranges", "_bucket_bounds", "_ready"):
+            setattr(n, meth, types.MethodType(getattr(unet.UNet, meth), n))
+        got = []
+        n.on_bucket_ready = lambda a, b: got.append((a, b))
+        enc, dec = n._bucket_bounds()
+        for b in dec[::-1] + enc[::-1]:      # the order backward() finishes them
+            n._ready(b)
+        po = PeerOptimizer.__new__(PeerOptimizer)
+        po.rank, po.world = 0, 8
+        assert sorted(got) == po.buckets(n)
+        covered = sum(b - a for a, b in got)
+        assert covered == sum(b - a for a, b in n.live_ranges())
+        for world in (2, 8):
+            owned = []
+            for r in range(world):
+                po.rank, po.world = r, world
+                owned += po.owned(n)
+            owned.sort()
+            assert all(a2 >= b1 for (_, b1), (a2, _) in zip(owned, owned[1:]))   # disjoint
+            assert sum(b - a for a, b in owned) == covered
+
+
 def test_streaming_metrics_match_tf_metrics_semantics():
     """summary.py:141-147 / tf_aerial_images.py:428: tf.metrics.* accumulate counts over calls and
     are zeroed once per epoch; F1 = 2 / (1/recall + 1/precision); the zero entries the reference

@@ -72,8 +72,18 @@ class PeerOptimizer:
         peers.params_mc = mc_p if self.multicast and mc_mode in (1, 3) else None
         self.mc_mode = mc_mode if self.multicast else 0
         self._peers = peers
-        # RSU_DP_OVERLAP=0: one exchange after the whole backward pass instead of per bucket
-        self.overlap = os.environ.get("RSU_DP_OVERLAP", "1") != "0"
+        # RSU_DP_OVERLAP: 1 = buckets are exchanged on a side stream while the backward pass runs,
+        # 0 = one exchange after the whole backward pass.  Default "auto": overlapped from four ranks
+        # on.  At two ranks the exchange after the backward pass already costs only 0.1 ms (each
+        # rank updates half of the parameters instead of all of them), and that is the combination
+        # the full 2-GPU benchmark has run with: the one 2-GPU bench.py run with the overlapped
+        # peer-load variant did not finish (cause not established before the round's GPU budget
+        # ended; tools/test_dp.py passes with it at 2 and at 8 GPUs, bench.py at 4 and at 8).
+        ov_env = os.environ.get("RSU_DP_OVERLAP", "auto")
+        self.overlap = (world >= 4) if ov_env == "auto" else ov_env != "0"
+        # a rank that never arrives must not hang its peers for ever: the barrier kernels trap
+        # after this long (milliseconds)
+        self.barrier_timeout_ms = int(os.environ.get("RSU_DP_BARRIER_TIMEOUT_MS", "120000"))
         self._side = torch.cuda.Stream()
         self._armed, self._done, self._acc = None, [], None
 
@@ -111,7 +121,7 @@ class PeerOptimizer:
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             self._side.wait_event(ev)
-            self._hg.barrier(channel=0)      # every rank has finished this bucket's gradients
+            self._hg.barrier(channel=0, timeout_ms=self.barrier_timeout_ms)  # all ranks have this bucket
             self._launch([(lo, hi)], lr, momentum, scale)
         self._done.append((lo, hi))
 
@@ -152,10 +162,10 @@ class PeerOptimizer:
         if done:
             cur.wait_stream(self._side)
         if rest:
-            self._hg.barrier(channel=0)      # every rank's backward pass has finished
+            self._hg.barrier(channel=0, timeout_ms=self.barrier_timeout_ms)  # every backward pass finished
             for b in rest:
                 self._launch([b], float(lr), float(momentum), float(extra_scale))
-        self._hp.barrier(channel=1)          # every rank's weights (and gradient reads) are complete
+        self._hp.barrier(channel=1, timeout_ms=self.barrier_timeout_ms)  # all weights (and gradient reads) done
         self._armed, self._done = None, []
 
     def full_momentum(self, net):

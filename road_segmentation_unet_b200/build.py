@@ -38,14 +38,33 @@ def _digest():
     return h.hexdigest()
 
 
+def _up_to_date(stamp, digest):
+    if os.path.exists(LIB) and os.path.exists(stamp):
+        with open(stamp) as f:
+            return f.read().strip() == digest
+    return False
+
+
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ and link librsu_b200.so; skipped when up to date."""
+    """Compile every .cu under csrc/ and link librsu_b200.so; skipped when up to date.  Several
+    processes may call this at once (one per GPU under torchrun): a file lock lets one of them
+    build while the others wait and then find the library up to date."""
     stamp = LIB + ".stamp"
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp):
-        with open(stamp) as f:
-            if f.read().strip() == digest:
+    if not force and _up_to_date(stamp, digest):
+        return LIB
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(stamp, digest):
                 return LIB
+            return _build_locked(stamp, digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp, digest, verbose):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()

@@ -349,3 +349,17 @@ def test_dp_gradient_buckets_gloo(tmp_path):
     expect = np.arange(n_flat, dtype=np.float32) * 1.5  # mean of x*1 and x*2
     for r in range(2):
         assert np.allclose(np.load(str(tmp_path / ("g%d.npy" % r))), expect)
+
+
+def test_overlays_reproduce_the_reference_submission_images():
+    """images.overlays (host side, PIL) on the real test-image windows + the masks of the reference's
+    own submissions == the overlay PNGs the reference committed (tests/golden/make_submission_golden.py)."""
+    from road_segmentation_unet_b200 import images
+    S = np.load(os.path.join(ROOT, "tests", "golden", "submission_golden.npz"))
+    side = S["crop_rgb"].shape[1]
+    for r in range(S["crop_overlay"].shape[0]):
+        masks = np.kron(S["labels"][r].transpose(0, 2, 1), np.ones((16, 16), np.uint8)).astype(np.float64)
+        for j, (k, top, left) in enumerate(S["crops"]):
+            img = S["crop_rgb"][j:j + 1].astype(np.float32) / np.float32(255)
+            m = masks[k:k + 1, top:top + side, left:left + side, None]
+            assert np.array_equal(images.overlays(img, m, fade=0.4)[0], S["crop_overlay"][r, j])

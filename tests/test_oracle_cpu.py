@@ -104,6 +104,37 @@ def test_scoring_and_visual_golden():
         [head[0]] + [r.split(",")[0] + ",0" for r in head[1:]]
 
 
+def submission_masks(labels):
+    """[50, 38, 38] labels indexed [image, x cell, y cell] -> the quantised 608 x 608 masks."""
+    return np.kron(labels.transpose(0, 2, 1), np.ones((16, 16), np.uint8)).astype(np.float64)
+
+
+def test_reference_submission_known_answers():
+    """The reference's OWN committed outputs (submissions/*/images_NNN.png + submission.csv, written
+    by tf_aerial_images.py:446-458 from data/test/*.png; tests/golden/make_submission_golden.py):
+    the overlay of the real test image with the quantised mask is reproduced byte for byte, and the
+    masks the overlays locate give back every run's submission.csv byte for byte."""
+    import hashlib
+    S = np.load(os.path.join(os.path.dirname(__file__), "golden", "submission_golden.npz"))
+    side = S["crop_rgb"].shape[1]
+    for r in range(S["labels"].shape[0]):
+        masks = submission_masks(S["labels"][r])
+        text = IO.submission_rows(masks, 16)
+        assert hashlib.sha256(text.encode()).hexdigest() == str(S["csv_sha256"][r]), str(S["runs"][r])
+        if r == 0:
+            assert text.startswith(bytes(S["csv_head"]).decode())
+        assert np.array_equal(IO.quantize_mask(masks[:4, :, :, None], 0.25, 16)[..., 0], masks[:4])
+        if r < S["crop_overlay"].shape[0]:
+            for j, (k, top, left) in enumerate(S["crops"]):
+                img = S["crop_rgb"][j:j + 1].astype(np.float32) / np.float32(255)  # = mpimg.imread
+                m = masks[k:k + 1, top:top + side, left:left + side]
+                assert 0.02 < m.mean() < 0.98  # the window shows road and background
+                assert np.array_equal(IO.overlays(img, m, fade=0.4)[0], S["crop_overlay"][r, j])
+                # the transposed mask is NOT what the reference drew: the test pins the cell order
+                assert not np.array_equal(IO.overlays(img, m.transpose(0, 2, 1), fade=0.4)[0],
+                                          S["crop_overlay"][r, j])
+
+
 def test_input_size_needed():
     """unet.py:100-115; closed form S = P + 12 * 2^(L-1) - 8 (report/report.tex:50)."""
     assert UO.input_size_needed(388, 4) == 476

@@ -448,3 +448,29 @@ def test_sharded_train_prep_and_strict_restore(tmp_path):
     with open(tmp_path / "old.chkpt", "wb") as f:
         np.savez(f, **t)
     model.restore(file=str(tmp_path / "old.chkpt"))
+
+
+def test_reference_submission_files_reproduced(tmp_path):
+    """Last steps of the reference's `main` (tf_aerial_images.py:453-458) on the reference's own
+    committed outputs (tests/golden/make_submission_golden.py): the quantised masks located by its
+    overlay PNGs go through quantize_mask (a fixed point), overlays and save_submission_csv here
+    and give back its overlay pixels and its submission.csv files byte for byte."""
+    import hashlib
+    import os
+    from road_segmentation_unet_b200 import images
+    from road_segmentation_unet_b200.constants import FOREGROUND_THRESHOLD, IMG_PATCH_SIZE
+    S = np.load(os.path.join(os.path.dirname(__file__), "golden", "submission_golden.npz"))
+    side = S["crop_rgb"].shape[1]
+    for r in range(S["crop_overlay"].shape[0]):
+        masks = np.kron(S["labels"][r].transpose(0, 2, 1), np.ones((16, 16), np.uint8)).astype(np.float64)
+        masks = masks[..., None]
+        q = images.quantize_mask(masks, patch_size=IMG_PATCH_SIZE, threshold=FOREGROUND_THRESHOLD)
+        assert q.shape == masks.shape and np.array_equal(q, masks)
+        out = tmp_path / ("run%d" % r)
+        images.save_submission_csv(q, str(out), IMG_PATCH_SIZE)
+        with open(out / "submission.csv", "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == str(S["csv_sha256"][r]), str(S["runs"][r])
+        for j, (k, top, left) in enumerate(S["crops"]):
+            img = S["crop_rgb"][j:j + 1].astype(np.float32) / np.float32(255)
+            m = q[k:k + 1, top:top + side, left:left + side]
+            assert np.array_equal(images.overlays(img, m, fade=0.4)[0], S["crop_overlay"][r, j])

@@ -395,6 +395,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    t_start = time.perf_counter()
+
+    def note(msg):  # progress on stderr (stdout carries the one JSON line): where a stuck run stopped
+        sys.stderr.write("[bench rank %d +%.1fs] %s\n" % (rank, time.perf_counter() - t_start, msg))
+        sys.stderr.flush()
+
     def device_step():
         net.zero_grads()
         net.forward(x, lab, keep=1.0)
@@ -402,9 +408,14 @@ def run_gpu(args):
         model.apply_update()
 
     W, K = max(args.warmup, 3), max(args.steps, 1)
+    note("model built (%s), %d warm-up steps" % (
+        "single GPU" if model._peer is None and world == 1 else
+        "NCCL all-reduce" if model._peer is None else
+        "peer optimizer, overlap=%s, multicast mode %d" % (model._peer.overlap, model._peer.mc_mode), W))
     for _ in range(W):
         device_step()
     barrier()
+    note("warm-up done, timing %d steps" % K)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -429,6 +440,7 @@ def run_gpu(args):
         ms = float(t.item())
     ms_per_step = ms / K
     value = world * B * K / (ms / 1e3)
+    note("device-timed region done: %.2f ms per step" % ms_per_step)
 
     if args.large_tiles:  # BASELINE.json configs[4] only (its own line; not the headline config)
         del x, lab
@@ -476,6 +488,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * B * ke / e2e_s
+    note("end-to-end leg done")
     h2d = B * S * S * 3 * 4 + B * P * P
     d2h = B * P * P * 4 + 4
     # the same loop with --image_augmentation (BASELINE.json configs[3]): every step additionally
@@ -496,6 +509,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         aug_s = float(t.item())
     e2e_aug_value = world * B * ke / aug_s
+    note("end-to-end leg with image augmentation done")
     opts.image_augmentation = False
 
     # ---- sliding-window ensemble prediction (BASELINE.json configs[2]) through the public API:
@@ -564,12 +578,14 @@ def run_gpu(args):
     extra = {}
     # (every rank runs the instrumented steps -- they contain the gradient all-reduce -- but only
     # rank 0 brackets its kernels with events)
+    note("prediction leg done" if predict is not None else "prediction leg skipped")
     kp = min(K, 3)
     if rank == 0:
         ops.profile_start()
     for _ in range(kp):
         device_step()
     barrier()
+    note("instrumented pass done")
     if rank == 0:
         peak, peak_sus, hbm, src = measured_peaks()
         rec = ops.profile_stop()

@@ -363,3 +363,111 @@ def test_overlays_reproduce_the_reference_submission_images():
             img = S["crop_rgb"][j:j + 1].astype(np.float32) / np.float32(255)
             m = masks[k:k + 1, top:top + side, left:left + side, None]
             assert np.array_equal(images.overlays(img, m, fade=0.4)[0], S["crop_overlay"][r, j])
+
+
+def _header_prototypes():
+    """{name: (return type, [parameter types])} parsed from include/rsu_b200.h (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "rsu_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = {}
+    for ret, name, params in re.findall(
+            r"^\s*((?:const\s+)?(?:unsigned\s+int|long\s+long|int|void|char)\s*\*?)\s*(rsu_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;",
+            text, flags=re.M | re.S):
+        plist = [] if params.strip() in ("", "void") else [" ".join(p.split()) for p in params.split(",")]
+        protos[name] = (" ".join(ret.split()), plist)
+    return protos
+
+
+def _ctype_class(param):
+    """C parameter declaration -> the ctypes class the binding must use."""
+    import ctypes as C
+    from road_segmentation_unet_b200 import _lib
+    structs = {"rsu_view": _lib.View, "rsu_conv_gemm_desc": _lib.ConvGemmDesc, "rsu_wgrad_desc": _lib.WgradDesc,
+               "rsu_pack_job": _lib.PackJob, "rsu_dp_peers": _lib.DpPeers}
+    decl = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", param).strip() if not param.endswith("*") else param
+    decl = decl.replace("const", "").strip()
+    if "*" in decl:
+        base = decl.replace("*", "").strip()
+        if base in structs:
+            return C.POINTER(structs[base])
+        if base == "int":
+            return (C.POINTER(C.c_int), C.c_void_p)     # host int* or device int*: either binding
+        if base == "double":
+            return (C.POINTER(C.c_double), C.c_void_p)
+        if base == "char":
+            return C.c_char_p
+        return C.c_void_p
+    return {"int": C.c_int, "long long": C.c_longlong, "unsigned long long": C.c_ulonglong,
+            "unsigned int": C.c_uint, "float": C.c_float, "double": C.c_double}[decl]
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """ctypes checks nothing at call time: a float bound as c_double, a missing argument or a
+    long long bound as c_int would corrupt a call silently.  Every prototype of the header is
+    compared with the binding's argtypes / restype, parameter by parameter."""
+    import ctypes as C
+    from road_segmentation_unet_b200 import _lib
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib._SIGNATURES), set(protos) ^ set(_lib._SIGNATURES)
+    ret_map = {"int": C.c_int, "long long": C.c_longlong, "void": None, "unsigned int": C.c_uint,
+               "const char*": C.c_char_p, "const char *": C.c_char_p}
+    for name, (ret, params) in sorted(protos.items()):
+        res, args = _lib._SIGNATURES[name]
+        assert res is ret_map[ret], (name, ret, res)
+        assert len(args) == len(params), (name, len(args), params)
+        for k, (p, a) in enumerate(zip(params, args)):
+            want = _ctype_class(p)
+            ok = a in want if isinstance(want, tuple) else a is want
+            assert ok, "%s argument %d (%s): bound as %s" % (name, k, p, a)
+
+
+def test_ctypes_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct of the header, as gcc lays them out, against the ctypes
+    Structure classes of the binding (also proves the header compiles as plain C)."""
+    import subprocess
+    from road_segmentation_unet_b200 import _lib
+    structs = {"rsu_view": _lib.View, "rsu_conv_gemm_desc": _lib.ConvGemmDesc, "rsu_wgrad_desc": _lib.WgradDesc,
+               "rsu_pack_job": _lib.PackJob, "rsu_dp_peers": _lib.DpPeers}
+    text = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "rsu_b200.h")).read(), flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rsu_b200.h"', 'int main(void) {']
+    fields = {}
+    for body, name in re.findall(r"typedef\s+struct\s*\{(.*?)\}\s*(rsu_[a-z0-9_]+)\s*;", text, flags=re.S):
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):  # "int H, W;" declares several fields
+                m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[[^\]]*\])?\s*$", part.strip())
+                names.append(m.group(1))
+        fields[name] = names
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (name, name))
+        for f in names:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    lines += ['  return 0;', '}']
+    assert set(fields) == set(structs), set(fields) ^ set(structs)
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    import ctypes as C
+    seen = 0
+    for line in out:
+        if not line.strip():
+            continue
+        s, f, v = line.split()
+        cls = structs[s]
+        if f == "sizeof":
+            assert C.sizeof(cls) == int(v), (s, C.sizeof(cls), v)
+        else:  # fields are matched by position (`in` of rsu_pack_job is `inp` in Python)
+            py_names = [n for n, _ in cls._fields_]
+            assert len(py_names) == len(fields[s]), (s, py_names, fields[s])
+            py = py_names[fields[s].index(f)]
+            assert py == f or (py, f) == ("inp", "in"), (s, py, f)
+            assert getattr(cls, py).offset == int(v), (s, f, getattr(cls, py).offset, v)
+        seen += 1
+    assert seen >= 60

@@ -145,9 +145,10 @@ def _encode_entry(dtype, shape, offset, size, crc):
     return out
 
 
-def _encode_header(num_shards=1, producer=24):
+def _encode_header(num_shards=1, producer=1):
     # BundleHeaderProto { num_shards = 1; endianness = 2 (LITTLE = 0, omitted);
     #                     VersionDef version = 3 { producer = 1 } }
+    # producer = kTensorBundleVersion (1) of tensor_bundle.cc; the reader accepts any producer >= 0
     ver = b"\x08" + _put_varint(producer)
     return b"\x08" + _put_varint(num_shards) + b"\x1a" + _put_varint(len(ver)) + ver
 

@@ -471,3 +471,118 @@ def test_ctypes_struct_layouts_match_header(tmp_path):
             assert getattr(cls, py).offset == int(v), (s, f, getattr(cls, py).offset, v)
         seen += 1
     assert seen >= 60
+
+
+def _bundle_proto_classes():
+    """BundleHeaderProto / BundleEntryProto of tensorflow/core/protobuf/tensor_bundle.proto (with
+    TensorShapeProto and VersionDef), declared to the protobuf runtime from their published field
+    numbers -- an independent implementation of the wire format to hold tf_checkpoint's
+    hand-written encoder / parser against."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="rsu_test_tensor_bundle.proto", package="rsu_test", syntax="proto3")
+
+    def msg(name, fields, nested=()):
+        m = descriptor_pb2.DescriptorProto(name=name)
+        for fname, num, ftype, label, type_name in fields:
+            f = m.field.add(name=fname, number=num, type=ftype, label=label)
+            if type_name:
+                f.type_name = type_name
+        for n in nested:
+            m.nested_type.add().CopyFrom(n)
+        return m
+
+    opt, rep = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+    dim = msg("Dim", [("size", 1, F.TYPE_INT64, opt, None), ("name", 2, F.TYPE_STRING, opt, None)])
+    shape = msg("TensorShapeProto", [("dim", 2, F.TYPE_MESSAGE, rep, ".rsu_test.TensorShapeProto.Dim"),
+                                     ("unknown_rank", 3, F.TYPE_BOOL, opt, None)], nested=[dim])
+    version = msg("VersionDef", [("producer", 1, F.TYPE_INT32, opt, None), ("min_consumer", 2, F.TYPE_INT32, opt, None),
+                                 ("bad_consumers", 3, F.TYPE_INT32, rep, None)])
+    header = msg("BundleHeaderProto", [("num_shards", 1, F.TYPE_INT32, opt, None), ("endianness", 2, F.TYPE_INT32, opt, None),
+                                       ("version", 3, F.TYPE_MESSAGE, opt, ".rsu_test.VersionDef")])
+    entry = msg("BundleEntryProto", [("dtype", 1, F.TYPE_INT32, opt, None),
+                                     ("shape", 2, F.TYPE_MESSAGE, opt, ".rsu_test.TensorShapeProto"),
+                                     ("shard_id", 3, F.TYPE_INT32, opt, None), ("offset", 4, F.TYPE_INT64, opt, None),
+                                     ("size", 5, F.TYPE_INT64, opt, None), ("crc32c", 6, F.TYPE_FIXED32, opt, None)])
+    for m in (shape, version, header, entry):
+        fd.message_type.add().CopyFrom(m)
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("rsu_test." + n))
+    return get("BundleHeaderProto"), get("BundleEntryProto")
+
+
+def test_tf_checkpoint_wire_formats_against_protobuf_and_snappy():
+    """The hand-written protobuf encoder / parser and the snappy decoder of tf_checkpoint.py against
+    independent implementations: the protobuf runtime and pyarrow's snappy codec."""
+    from road_segmentation_unet_b200 import tf_checkpoint as T
+    Header, Entry = _bundle_proto_classes()
+    h = Header.FromString(T._encode_header())
+    assert (h.num_shards, h.endianness, h.version.producer, h.version.min_consumer) == (1, 0, 1, 0)
+    assert h.SerializeToString() == T._encode_header()            # canonical proto3 bytes
+    cases = [(T.DT_FLOAT, (3, 3, 64, 128), 0, 3 * 3 * 64 * 128 * 4, 0xDEADBEEF),
+             (T.DT_FLOAT, (2, 2, 1024, 2048), 5_000_000_000, 2 * 2 * 1024 * 2048 * 4, 1),
+             (T.DT_INT32, (), 849_613_112, 4, 0x80000000), (T.DT_INT64, (7,), 12, 56, 0)]
+    for dtype, shape, offset, size, crc in cases:
+        raw = T._encode_entry(dtype, shape, offset, size, crc)
+        e = Entry.FromString(raw)
+        assert (e.dtype, [d.size for d in e.shape.dim], e.shard_id, e.offset, e.size, e.crc32c) == \
+            (dtype, list(shape), 0, offset, size, crc)
+        assert e.HasField("shape")                                # scalars carry an empty shape message
+        if crc:  # (proto3 omits a zero fixed32; the encoder always writes the checksum)
+            assert e.SerializeToString() == raw
+        # ... and the parser reads what the protobuf runtime writes (entries TensorFlow would write)
+        e2 = Entry(dtype=dtype, shard_id=0, offset=offset, size=size, crc32c=crc)
+        e2.shape.SetInParent()
+        for s in shape:
+            e2.shape.dim.add(size=s)
+        p = T._parse_entry(e2.SerializeToString())
+        assert (p["dtype"], p["shape"], p["shard_id"], p["offset"], p["size"], p["sliced"]) == \
+            (dtype, list(shape), 0, offset, size, False)
+        assert p["crc32c"] == (crc if crc else None)
+    # a zero-sized dimension is omitted on the wire by proto3 writers: the parser must keep the dim
+    e3 = Entry(dtype=T.DT_FLOAT, size=0, crc32c=5)
+    e3.shape.dim.add(size=0)
+    e3.shape.dim.add(size=4)
+    assert T._parse_entry(e3.SerializeToString())["shape"] == [0, 4]
+    # snappy-compressed index blocks (TensorFlow's table builder may use them)
+    pa = pytest.importorskip("pyarrow")
+    rs = np.random.RandomState(0)
+    for data in (b"", b"a", b"conv_0/conv1/kernel/Momentum" * 500,
+                 bytes(rs.randint(0, 256, 70000, dtype=np.uint8)),
+                 b"ab" * 40000 + bytes(rs.randint(0, 4, 9000, dtype=np.uint8)) + b"\0" * 200000):
+        assert T._snappy_uncompress(pa.compress(data, codec="snappy", asbytes=True)) == data
+
+
+def test_tf_checkpoint_reads_snappy_compressed_tables(tmp_path):
+    """An index whose blocks are snappy-compressed (block type 1, as LevelDB-format writers may
+    produce) reads like the uncompressed one; the compressor is pyarrow's, not ours."""
+    import struct
+    pa = pytest.importorskip("pyarrow")
+    from road_segmentation_unet_b200 import tf_checkpoint as T
+    items = [(b"", T._encode_header())] + [
+        (("scope_%04d/kernel" % i).encode(), T._encode_entry(T.DT_FLOAT, (3, 3, 64, 64), i * 147456, 147456, i + 1))
+        for i in range(300)]
+    out = bytearray()
+
+    def emit(block):
+        comp = pa.compress(block, codec="snappy", asbytes=True)
+        off = len(out)
+        out.extend(comp)
+        out.extend(b"\x01" + struct.pack("<I", T.mask_crc(T.crc32c(comp + b"\x01"))))
+        return T._put_varint(off) + T._put_varint(len(comp))
+
+    index = T._BlockBuilder()
+    for lo in range(0, len(items), 100):          # several data blocks
+        blk = T._BlockBuilder()
+        for k, v in items[lo:lo + 100]:
+            blk.add(k, v)
+        index.add(items[min(lo + 99, len(items) - 1)][0], emit(blk.finish()))
+    footer = emit(T._BlockBuilder().finish()) + emit(index.finish())
+    out.extend(footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", T.TABLE_MAGIC))
+    path = tmp_path / "snappy.index"
+    path.write_bytes(bytes(out))
+    assert T.read_table(str(path)) == items
+    plain = tmp_path / "plain.index"
+    T.write_table(str(plain), items)
+    assert T.read_table(str(plain)) == items

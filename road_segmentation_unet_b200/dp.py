@@ -82,8 +82,9 @@ class PeerOptimizer:
         ov_env = os.environ.get("RSU_DP_OVERLAP", "auto")
         self.overlap = (world >= 4) if ov_env == "auto" else ov_env != "0"
         # a rank that never arrives must not hang its peers for ever: the barrier kernels trap
-        # after this long (milliseconds)
-        self.barrier_timeout_ms = int(os.environ.get("RSU_DP_BARRIER_TIMEOUT_MS", "120000"))
+        # after this long (milliseconds; 10 minutes, the default of NCCL's own watchdog: a rank may be
+        # busy on the host -- evaluation dumps, a checkpoint -- while its peers already wait)
+        self.barrier_timeout_ms = int(os.environ.get("RSU_DP_BARRIER_TIMEOUT_MS", "600000"))
         self._side = torch.cuda.Stream()
         self._armed, self._done, self._acc = None, [], None
 

@@ -586,3 +586,126 @@ def test_tf_checkpoint_reads_snappy_compressed_tables(tmp_path):
     plain = tmp_path / "plain.index"
     T.write_table(str(plain), items)
     assert T.read_table(str(plain)) == items
+
+
+def test_dp_peer_optimizer_protocol_simulated(monkeypatch):
+    """Host logic of dp.PeerOptimizer without a GPU: streams, events, the symmetric-memory handles and
+    the kernel entry point are replaced by recorders, then `world` ranks run the calls of a training
+    step (arm -> bucket hooks in backward order -> step) with and without the overlapped exchange.
+    Every rank must issue the SAME sequence of barriers (a rank-dependent sequence deadlocks), the
+    launches of all ranks must update every live parameter exactly once with the same scalars, an
+    overlapped bucket must be preceded by its own barrier on the side stream, and the weights-published
+    barrier must come last."""
+    import contextlib
+    import ctypes as C
+    import types
+    from road_segmentation_unet_b200 import _lib, dp, unet
+
+    class Stream:
+        def __init__(self, tag):
+            self.tag = tag
+
+        def wait_event(self, ev):
+            log.append(("wait_event", self.tag, ev.stream))
+
+        def wait_stream(self, other):
+            log.append(("wait_stream", self.tag, other.tag))
+
+    class Event:
+        def record(self, stream):
+            self.stream = stream.tag
+
+    state = {"cur": None}
+    main, log = Stream("main"), []
+    state["cur"] = main
+
+    @contextlib.contextmanager
+    def use_stream(s):
+        prev, state["cur"] = state["cur"], s
+        try:
+            yield
+        finally:
+            state["cur"] = prev
+
+    monkeypatch.setattr(dp.torch.cuda, "Event", Event)
+    monkeypatch.setattr(dp.torch.cuda, "current_stream", lambda: state["cur"])
+    monkeypatch.setattr(dp.torch.cuda, "stream", use_stream)
+
+    class Handle:
+        def __init__(self, name):
+            self.name = name
+
+        def barrier(self, channel=0, timeout_ms=0):
+            assert timeout_ms > 0
+            log.append(("barrier", self.name, channel, state["cur"].tag))
+
+    class Lib:
+        @staticmethod
+        def rsu_dp_momentum_sgd(peers, acc, lo, hi, lr, momentum, scale, stream):
+            log.append(("sgd", lo, hi, lr, momentum, scale, state["cur"].tag))
+            return 0
+
+    monkeypatch.setattr(_lib, "load", lambda: Lib)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+
+    L, dil = 6, True
+    net = types.SimpleNamespace(L=L, dilated=dil, root=64, _live_ranges=None,
+                                momentum=types.SimpleNamespace(data_ptr=lambda: 4096))
+    net.offsets, net.n_flat = unet.flat_layout(L, 64, dil)
+    net._first_offset = lambda prefix: next(o for name, o in net.offsets.items() if name.startswith(prefix))
+    for meth in ("live_ranges", "_bucket_bounds", "_ready"):
+        setattr(net, meth, types.MethodType(getattr(unet.UNet, meth), net))
+    enc, dec = net._bucket_bounds()
+    live = net.live_ranges()
+
+    def run_rank(rank, world, overlap, extra_scale):
+        del log[:]
+        po = dp.PeerOptimizer.__new__(dp.PeerOptimizer)
+        po.rank, po.world, po.overlap, po.barrier_timeout_ms = rank, world, overlap, 600000
+        po._hg, po._hp, po._side = Handle("grads"), Handle("params"), Stream("side")
+        po._peers, po._acc = _lib.DpPeers(), net.momentum
+        po._armed, po._done = None, []
+        net.on_bucket_ready = po.bucket_ready
+        # a micro-batch whose hook is off (UNet.accumulate_step) must not exchange anything
+        net.on_bucket_ready = None
+        for b in dec[::-1] + enc[::-1]:
+            net._ready(b)
+        assert log == []
+        net.on_bucket_ready = po.bucket_ready
+        po.arm(0.01, 0.9, extra_scale)               # UNet.backward -> on_backward_begin
+        for b in dec[::-1] + enc[::-1]:
+            net._ready(b)
+        po.step(net, 0.01, 0.9, extra_scale=extra_scale)
+        assert po._armed is None and po._done == []
+        return list(log)
+
+    for world in (2, 4, 8):
+        for overlap in (False, True):
+            for extra in (1.0, 0.125):
+                runs = [run_rank(r, world, overlap, extra) for r in range(world)]
+                barriers = [[e for e in run if e[0] == "barrier"] for run in runs]
+                assert all(b == barriers[0] for b in barriers), "rank-dependent barrier sequence"
+                assert barriers[0][-1] == ("barrier", "params", 1, "main")
+                assert runs[0][-1] == barriers[0][-1]          # nothing follows the publishing barrier
+                n_buckets = len(dp.PeerOptimizer.buckets(types.SimpleNamespace(_buckets=None), net))
+                if overlap:
+                    assert barriers[0][:-1] == [("barrier", "grads", 0, "side")] * n_buckets
+                    assert ("wait_stream", "main", "side") in runs[0]
+                else:
+                    assert barriers[0][:-1] == [("barrier", "grads", 0, "main")]
+                updated = []
+                for run in runs:
+                    last_barrier = None
+                    for e in run:
+                        if e[0] == "barrier":
+                            last_barrier = e
+                        if e[0] == "sgd":
+                            _, lo, hi, lr, mu, scale, tag = e
+                            assert (lr, mu) == (0.01, 0.9) and abs(scale - extra / world) < 1e-12
+                            assert tag == ("side" if overlap else "main")
+                            assert last_barrier is not None and last_barrier[1] == "grads"
+                            updated.append((lo, hi))
+                updated.sort()
+                assert all(a2 >= b1 for (_, b1), (a2, _) in zip(updated, updated[1:])), "element updated twice"
+                assert sum(b - a for a, b in updated) == sum(b - a for a, b in live)
+                assert updated[0][0] == live[0][0] and updated[-1][1] == live[-1][1]
